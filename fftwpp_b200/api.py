@@ -1,0 +1,162 @@
+"""Python mirror of the reference's wrapper classes (reference wrappers/fftwpp.py)
+over the generic handle API of lib_fftwpp.so.
+
+Arrays are numpy arrays (host; staged through the device by the library) or
+torch CUDA tensors (device; convolved in place, asynchronously on the current
+library stream).
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import lib
+
+KIND_COMPLEX, KIND_CENTERED, KIND_HERMITIAN, KIND_REAL = 0, 1, 2, 3
+MULT_NONE, MULT_BINARY, MULT_REALBINARY, MULT_CORRELATION = 0, 1, 2, 3
+FAMILY_COMPLEX, FAMILY_HERMITIAN, FAMILY_REAL = 0, 1, 2
+
+_INFO = ("L M C S m p q n R dr D D0 l b inplace overwrite centered inputLength "
+         "wordSize doubles outputSize workSizeW workSizeV nloops loop2 conjugates "
+         "residueBlocks paddedSize normalization repad allRows").split()
+
+
+def _ptr(a):
+    """Raw data pointer of a numpy array or torch tensor."""
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("arrays must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise ValueError("tensors must be contiguous")
+        return a.data_ptr()
+    raise TypeError("expected a numpy array or a torch tensor")
+
+
+def launch_count():
+    """Number of CUDA kernels this library has launched in this process."""
+    return int(lib.fftwpp_gpu_launch_count())
+
+
+def set_stream(cuda_stream):
+    """Use the given cudaStream_t (int) for all subsequent launches."""
+    lib.fftwpp_set_stream(ctypes.c_void_p(cuda_stream))
+
+
+class Pad:
+    """One padded FFT (reference fftPad / fftPadCentered / fftPadHermitian /
+    fftPadReal, convolve.h:471-980) with the accessors tests/hybrid*.cc walk."""
+
+    def __init__(self, kind, L, M, C=1, S=0, m=0, D=0, I=-1, A=1, B=1, mult=MULT_NONE):
+        self.kind = kind
+        self._h = lib.fftwpp_pad_create(kind, L, M, C, S, m, D, I, A, B, mult)
+        buf = (ctypes.c_size_t * 32)()
+        lib.fftwpp_pad_info(self._h, buf)
+        self.info = dict(zip(_INFO, [int(v) for v in buf]))
+        for k, v in self.info.items():
+            setattr(self, k, v)
+
+    def close(self):
+        if self._h:
+            lib.fftwpp_pad_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def increment(self, r):
+        return int(lib.fftwpp_pad_increment(self._h, r))
+
+    def blocksize(self, r):
+        return int(lib.fftwpp_pad_blocksize(self._h, r))
+
+    def noutputs(self, r):
+        return int(lib.fftwpp_pad_noutputs(self._h, r))
+
+    def span(self, r):
+        return int(lib.fftwpp_pad_span(self._h, r))
+
+    def index(self, r, i):
+        return int(lib.fftwpp_pad_index(self._h, r, i))
+
+    def residue_calls(self):
+        r = 0
+        out = []
+        while r < self.R:
+            out.append(r)
+            r += self.increment(r)
+        return out
+
+    def forward(self, f, r=0, F=None):
+        """fft->forward(f,F,r): returns F (outputSize Complex words)."""
+        if F is None:
+            F = np.zeros(self.outputSize, dtype=np.complex128)
+        lib.fftwpp_pad_forward(self._h, _ptr(f), _ptr(F), r)
+        return F
+
+    def backward(self, F, f, r=0):
+        """fft->backward(F,f,r): assigns for r == 0, accumulates for r > 0."""
+        lib.fftwpp_pad_backward(self._h, _ptr(F), _ptr(f), r)
+        return f
+
+
+class HybridConv:
+    """Hybrid dealiased convolution in 1, 2 or 3 dimensions.
+
+    family 0: complex (reference HybridConvolution{,2,3}),
+    family 1: centered Hermitian (HybridConvolutionHermitian{,2,3}),
+    family 2: real input (tests/hybridconvr{,2,3}.cc object graph).
+    """
+
+    def __init__(self, L, M=None, family=FAMILY_COMPLEX, m=None, D=None, I=None,
+                 Sx=0, Sy=0, A=2, B=1, mult=None):
+        L = [int(v) for v in (L if hasattr(L, "__len__") else [L])]
+        dim = len(L)
+        if M is None:
+            if family == FAMILY_HERMITIAN:
+                M = [3 * ((l + 1) // 2) - 2 * (l % 2) for l in L]
+            else:
+                M = [A * l - A + 1 for l in L]
+        M = [int(v) for v in (M if hasattr(M, "__len__") else [M])]
+        if mult is None:
+            mult = MULT_REALBINARY if family == FAMILY_HERMITIAN else MULT_BINARY
+        arr = ctypes.c_size_t * dim
+        larr = ctypes.c_long * dim
+        m = arr(*([0] * dim if m is None else [int(v) for v in m]))
+        D = arr(*([0] * dim if D is None else [int(v) for v in D]))
+        I = larr(*([-1] * dim if I is None else [int(v) for v in I]))
+        self.dim, self.family, self.L, self.M, self.A, self.B = dim, family, L, M, A, B
+        self._h = lib.fftwpp_conv_create(dim, family, arr(*L), arr(*M), m, D, I,
+                                         Sx, Sy, A, B, mult)
+        self.doubles = int(lib.fftwpp_conv_doubles(self._h))
+
+    def close(self):
+        if self._h:
+            lib.fftwpp_conv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def params(self, d):
+        buf = (ctypes.c_size_t * 8)()
+        lib.fftwpp_conv_params(self._h, d, buf)
+        return dict(zip("m p q n D inplace C S".split(), [int(v) for v in buf]))
+
+    def set_plane_chunk(self, chunk):
+        lib.fftwpp_conv_set_plane_chunk(self._h, int(chunk))
+
+    def convolve(self, arrays, normalized=True):
+        """In-place convolution: the B outputs overwrite arrays[0:B]."""
+        n = max(self.A, self.B)
+        if len(arrays) < n:
+            raise ValueError("need %d arrays" % n)
+        ptrs = (ctypes.c_void_p * n)(*[_ptr(a) for a in arrays[:n]])
+        lib.fftwpp_conv_convolve(self._h, ptrs, 1 if normalized else 0)
+        return arrays[0] if self.B == 1 else arrays[:self.B]

@@ -1,0 +1,363 @@
+// cfftwpp.cc -- C-callable API (include/cfftwpp.h) over the host classes.
+// Part 1 mirrors the entry points defined by reference wrappers/cfftw++.cc
+// :27-163 and the owning bundles of wrappers/HybridConvolution.h:12-184
+// (default M = A*L-A+1 for complex, 3*ceil(L/2)-2*(L%2) for Hermitian).
+#include "convolve.h"
+#include "../../include/cfftwpp.h"
+#include "../../include/fftwpp_gpu.h"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace fftwpp;
+using namespace utils;
+
+namespace {
+
+multiplier *pickMult(int id)
+{
+  switch(id) {
+    case 1: return multBinary;
+    case 2: return realMultBinary;
+    case 3: return multcorrelation;
+  }
+  return multNone;
+}
+
+fftBase *makePad(int kind, size_t L, size_t M, Application &app, size_t C,
+                 size_t S, size_t m, size_t D, long I)
+{
+  bool forced=m > 0;
+  switch(kind) {
+    case 0:
+      return forced ? new fftPad(L,M,app,C,S,m,D,I != 0) :
+        new fftPad(L,M,app,C,S);
+    case 1:
+      return forced ?
+        (fftBase *) new fftPadCentered(L,M,app,C,S,m,D,I != 0) :
+        (fftBase *) new fftPadCentered(L,M,app,C,S);
+    case 2:
+      return forced ? (fftBase *) new fftPadHermitian(L,M,app,C,m,D,I != 0) :
+        (fftBase *) new fftPadHermitian(L,M,app,C);
+    case 3:
+      return forced ? (fftBase *) new fftPadReal(L,M,app,C,S,m,D,I != 0) :
+        (fftBase *) new fftPadReal(L,M,app,C,S);
+  }
+  std::cerr << "unknown padded-FFT kind " << kind << std::endl;
+  exit(-1);
+}
+
+struct Pad {
+  Application *app;
+  fftBase *fft;
+};
+
+// Generic convolution bundle (any dimension / family).
+struct Conv {
+  int dim;
+  Application *app[3];
+  fftBase *fft[3];
+  Convolution *c1;
+  Convolution2 *c2;
+  Convolution3 *c3;
+  size_t A,B;
+  size_t doubles;
+
+  Conv() : dim(0), c1(NULL), c2(NULL), c3(NULL), A(0), B(0), doubles(0) {
+    for(int d=0; d < 3; ++d) {app[d]=NULL; fft[d]=NULL;}
+  }
+
+  ~Conv() {
+    delete c1; delete c2; delete c3;
+    for(int d=2; d >= 0; --d) {
+      delete fft[d];
+      delete app[d];
+    }
+  }
+
+  void convolve(Complex **f, bool normalized) {
+    if(c1) {if(normalized) c1->convolve(f); else c1->convolveRaw(f);}
+    if(c2) {if(normalized) c2->convolve(f); else c2->convolveRaw(f);}
+    if(c3) {if(normalized) c3->convolve(f); else c3->convolveRaw(f);}
+  }
+};
+
+Conv *makeConv(int dim, int family, const size_t *L, const size_t *M,
+               const size_t *m, const size_t *D, const long *I, size_t Sx,
+               size_t Sy, size_t A, size_t B, int mult)
+{
+  if(dim < 1 || dim > 3) {
+    std::cerr << "dimension must be 1, 2 or 3" << std::endl;
+    exit(-1);
+  }
+  Conv *c=new Conv;
+  c->dim=dim;
+  c->A=A;
+  c->B=B;
+  int kinds[3];
+  size_t len[3];
+  for(int d=0; d < dim; ++d) {
+    if(family == 0) kinds[d]=0;
+    else if(family == 1) kinds[d]=(d == dim-1) ? 2 : 1;
+    else kinds[d]=(d == 0) ? 3 : 0;
+    len[d]=(family == 1 && d == dim-1) ? ceilquotient(L[d],2) : L[d];
+  }
+  size_t zero[3]={0,0,0};
+  long minus[3]={-1,-1,-1};
+  if(!m) m=zero;
+  if(!D) D=zero;
+  if(!I) I=minus;
+  for(int d=0; d < dim; ++d) {
+    multiplier *mu=(d == dim-1) ? pickMult(mult) : multNone;
+    long Id=m[d] > 0 ? I[d] : -1;
+    if(d == 0)
+      c->app[d]=new Application(A,B,mu,fftw::maxthreads,false,m[d],D[d],Id);
+    else
+      c->app[d]=new Application(A,B,mu,*c->app[d-1],m[d],D[d],Id);
+  }
+  if(dim == 1) {
+    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],1,0,m[0],D[0],I[0]);
+    c->c1=new Convolution(c->fft[0]);
+    c->doubles=c->fft[0]->doubles();
+  } else if(dim == 2) {
+    if(Sx == 0) Sx=len[1];
+    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],len[1],Sx,m[0],D[0],I[0]);
+    c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],1,0,m[1],D[1],I[1]);
+    c->c2=new Convolution2(c->fft[0],c->fft[1]);
+    c->doubles=c->fft[0]->wordSize()*L[0]*Sx;
+  } else {
+    if(Sy == 0) Sy=len[2];
+    if(Sx == 0) Sx=L[1]*Sy;
+    size_t Cx=(Sy == len[2] || kinds[0] == 3) ? L[1]*Sy : len[2];
+    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],Cx,Sx,m[0],D[0],I[0]);
+    c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],len[2],Sy,m[1],D[1],I[1]);
+    c->fft[2]=makePad(kinds[2],L[2],M[2],*c->app[2],1,0,m[2],D[2],I[2]);
+    c->c3=new Convolution3(c->fft[0],c->fft[1],c->fft[2]);
+    c->doubles=c->fft[0]->wordSize()*L[0]*Sx;
+  }
+  return c;
+}
+
+size_t defaultM(size_t L, size_t A) {return A*L-A+1;}
+size_t defaultMh(size_t L) {return 3*ceilquotient(L,2)-2*(L % 2);}
+
+Conv *simpleConv(int dim, int family, size_t Lx, size_t Ly, size_t Lz)
+{
+  size_t L[3]={Lx,Ly,Lz};
+  size_t M[3];
+  for(int d=0; d < dim; ++d)
+    M[d]=family == 1 ? defaultMh(L[d]) : defaultM(L[d],2);
+  return makeConv(dim,family,L,M,NULL,NULL,NULL,0,0,2,1,family == 1 ? 2 : 1);
+}
+
+void binary(Conv *c, fftwpp_cplx *a, fftwpp_cplx *b)
+{
+  Complex *F[]={(Complex *) a,(Complex *) b};
+  c->convolve(F,true);
+}
+
+} // namespace
+
+extern "C" {
+
+double *create_doubleAlign(size_t n) {return doubleAlign(n);}
+void delete_doubleAlign(double *p) {deleteAlign(p);}
+fftwpp_cplx *create_complexAlign(size_t n)
+{
+  return (fftwpp_cplx *) ComplexAlign(n);
+}
+void delete_complexAlign(fftwpp_cplx *p) {deleteAlign(p);}
+
+size_t get_fftwpp_maxthreads(void) {return fftw::maxthreads;}
+void set_fftwpp_maxthreads(size_t nthreads) {fftw::maxthreads=nthreads;}
+
+HybridConvolution *fftwpp_create_conv1d(size_t L)
+{
+  return (HybridConvolution *) simpleConv(1,0,L,0,0);
+}
+void fftwpp_conv1d_delete(HybridConvolution *conv) {delete (Conv *) conv;}
+void fftwpp_conv1d_convolve(HybridConvolution *conv, fftwpp_cplx *a,
+                            fftwpp_cplx *b)
+{
+  binary((Conv *) conv,a,b);
+}
+
+HybridConvolutionHermitian *fftwpp_create_hconv1d(size_t L)
+{
+  return (HybridConvolutionHermitian *) simpleConv(1,1,L,0,0);
+}
+void fftwpp_hconv1d_delete(HybridConvolutionHermitian *conv)
+{
+  delete (Conv *) conv;
+}
+void fftwpp_HermitianSymmetrize(fftwpp_cplx *f)
+{
+  HermitianSymmetrize((Complex *) f);
+}
+void fftwpp_hconv1d_convolve(HybridConvolutionHermitian *conv, fftwpp_cplx *a,
+                             fftwpp_cplx *b)
+{
+  binary((Conv *) conv,a,b);
+}
+
+HybridConvolution2 *fftwpp_create_conv2d(size_t Lx, size_t Ly)
+{
+  return (HybridConvolution2 *) simpleConv(2,0,Lx,Ly,0);
+}
+void fftwpp_conv2d_delete(HybridConvolution2 *conv) {delete (Conv *) conv;}
+void fftwpp_HermitianSymmetrizeX(size_t Hx, size_t Hy, size_t x0,
+                                 fftwpp_cplx *f)
+{
+  HermitianSymmetrizeX(Hx,Hy,x0,(Complex *) f);
+}
+void fftwpp_conv2d_convolve(HybridConvolution2 *conv, fftwpp_cplx *a,
+                            fftwpp_cplx *b)
+{
+  binary((Conv *) conv,a,b);
+}
+HybridConvolutionHermitian2 *fftwpp_create_hconv2d(size_t Lx, size_t Ly)
+{
+  return (HybridConvolutionHermitian2 *) simpleConv(2,1,Lx,Ly,0);
+}
+void fftwpp_hconv2d_delete(HybridConvolutionHermitian2 *conv)
+{
+  delete (Conv *) conv;
+}
+void fftwpp_hconv2d_convolve(HybridConvolutionHermitian2 *conv, fftwpp_cplx *a,
+                             fftwpp_cplx *b)
+{
+  binary((Conv *) conv,a,b);
+}
+
+HybridConvolution3 *fftwpp_create_conv3d(size_t Lx, size_t Ly, size_t Lz)
+{
+  return (HybridConvolution3 *) simpleConv(3,0,Lx,Ly,Lz);
+}
+void fftwpp_conv3d_delete(HybridConvolution3 *conv) {delete (Conv *) conv;}
+void fftwpp_HermitianSymmetrizeXY(size_t Hx, size_t Hy, size_t Hz, size_t x0,
+                                  size_t y0, fftwpp_cplx *f)
+{
+  HermitianSymmetrizeXY(Hx,Hy,Hz,x0,y0,(Complex *) f);
+}
+void fftwpp_conv3d_convolve(HybridConvolution3 *conv, fftwpp_cplx *a,
+                            fftwpp_cplx *b)
+{
+  binary((Conv *) conv,a,b);
+}
+HybridConvolutionHermitian3 *fftwpp_create_hconv3d(size_t Lx, size_t Ly,
+                                                   size_t Lz)
+{
+  return (HybridConvolutionHermitian3 *) simpleConv(3,1,Lx,Ly,Lz);
+}
+void fftwpp_hconv3d_delete(HybridConvolutionHermitian3 *conv)
+{
+  delete (Conv *) conv;
+}
+void fftwpp_hconv3d_convolve(HybridConvolutionHermitian3 *conv, fftwpp_cplx *a,
+                             fftwpp_cplx *b)
+{
+  binary((Conv *) conv,a,b);
+}
+
+// ---------------- generic handle API ----------------
+
+void *fftwpp_pad_create(int kind, size_t L, size_t M, size_t C, size_t S,
+                        size_t m, size_t D, long I, size_t A, size_t B,
+                        int mult)
+{
+  Pad *P=new Pad;
+  P->app=new Application(A,B,pickMult(mult),fftw::maxthreads,false,m,D,
+                         m > 0 ? I : -1);
+  P->fft=makePad(kind,L,M,*P->app,C,S,m,D,I);
+  return P;
+}
+
+void fftwpp_pad_destroy(void *pad)
+{
+  Pad *P=(Pad *) pad;
+  if(!P) return;
+  delete P->fft;
+  delete P->app;
+  delete P;
+}
+
+void fftwpp_pad_info(void *pad, size_t *out)
+{
+  fftBase *f=((Pad *) pad)->fft;
+  size_t i=0;
+  out[i++]=f->L; out[i++]=f->M; out[i++]=f->C; out[i++]=f->S;
+  out[i++]=f->m; out[i++]=f->p; out[i++]=f->q; out[i++]=f->n;
+  out[i++]=f->R; out[i++]=f->dr; out[i++]=f->D; out[i++]=f->D0;
+  out[i++]=f->l; out[i++]=f->b; out[i++]=f->inplace; out[i++]=f->overwrite;
+  out[i++]=f->centered; out[i++]=f->inputLength(); out[i++]=f->wordSize();
+  out[i++]=f->doubles(); out[i++]=f->outputSize(); out[i++]=f->workSizeW();
+  out[i++]=f->workSizeV(); out[i++]=f->nloops(); out[i++]=f->loop2();
+  out[i++]=f->conjugates(); out[i++]=f->residueBlocks();
+  out[i++]=f->paddedSize(); out[i++]=f->normalization(); out[i++]=f->repad();
+  out[i++]=f->allRows();
+  while(i < 32) out[i++]=0;
+}
+
+size_t fftwpp_pad_increment(void *pad, size_t r)
+{
+  return ((Pad *) pad)->fft->increment(r);
+}
+size_t fftwpp_pad_blocksize(void *pad, size_t r)
+{
+  return ((Pad *) pad)->fft->blocksize(r);
+}
+size_t fftwpp_pad_noutputs(void *pad, size_t r)
+{
+  return ((Pad *) pad)->fft->noutputs(r);
+}
+size_t fftwpp_pad_span(void *pad, size_t r)
+{
+  return ((Pad *) pad)->fft->span(r);
+}
+size_t fftwpp_pad_index(void *pad, size_t r, size_t i)
+{
+  return ((Pad *) pad)->fft->index(r,i);
+}
+
+void fftwpp_pad_forward(void *pad, const double *f, double *F, size_t r)
+{
+  ((Pad *) pad)->fft->forward((Complex *) f,(Complex *) F,r);
+}
+
+void fftwpp_pad_backward(void *pad, const double *F, double *f, size_t r)
+{
+  ((Pad *) pad)->fft->backward((Complex *) F,(Complex *) f,r);
+}
+
+void *fftwpp_conv_create(int dim, int family, const size_t *L, const size_t *M,
+                         const size_t *m, const size_t *D, const long *I,
+                         size_t Sx, size_t Sy, size_t A, size_t B, int mult)
+{
+  return makeConv(dim,family,L,M,m,D,I,Sx,Sy,A,B,mult);
+}
+
+void fftwpp_conv_destroy(void *conv) {delete (Conv *) conv;}
+
+void fftwpp_conv_params(void *conv, int d, size_t *out)
+{
+  fftBase *f=((Conv *) conv)->fft[d];
+  out[0]=f->m; out[1]=f->p; out[2]=f->q; out[3]=f->n; out[4]=f->D;
+  out[5]=f->inplace; out[6]=f->C; out[7]=f->S;
+}
+
+size_t fftwpp_conv_doubles(void *conv) {return ((Conv *) conv)->doubles;}
+
+void fftwpp_conv_convolve(void *conv, double **f, int normalized)
+{
+  ((Conv *) conv)->convolve((Complex **) f,normalized != 0);
+}
+
+void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk)
+{
+  Conv *c=(Conv *) conv;
+  if(c->c3) c->c3->convolveyz[0]->planeChunk=chunk;
+}
+
+void fftwpp_set_stream(void *stream) {gpu::setStream(stream);}
+
+}

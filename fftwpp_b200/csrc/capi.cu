@@ -1,0 +1,247 @@
+// capi.cu -- extern "C" entry points declared in include/fftwpp_gpu.h.
+#include "gpu_internal.h"
+
+#include <cstring>
+
+using namespace fftwpp_gpu;
+
+#define CUDA_TRY(call, what)                       \
+  do {                                             \
+    cudaError_t e_=(call);                         \
+    if(e_ != cudaSuccess) return cuda_fail(e_,what); \
+  } while(0)
+
+extern "C" {
+
+int fftwpp_gpu_device_count(void)
+{
+  int n=0;
+  cudaError_t e=cudaGetDeviceCount(&n);
+  if(e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fftwpp_gpu_set_device(int device)
+{
+  CUDA_TRY(cudaSetDevice(device),"cudaSetDevice");
+  return 0;
+}
+
+int fftwpp_gpu_malloc(void **ptr, size_t bytes)
+{
+  if(!ptr) return FFTWPP_GPU_EINVAL;
+  *ptr=NULL;
+  if(bytes == 0) return 0;
+  CUDA_TRY(cudaMalloc(ptr,bytes),"cudaMalloc");
+  return 0;
+}
+
+int fftwpp_gpu_free(void *ptr)
+{
+  if(!ptr) return 0;
+  CUDA_TRY(cudaFree(ptr),"cudaFree");
+  return 0;
+}
+
+int fftwpp_gpu_malloc_host(void **ptr, size_t bytes)
+{
+  if(!ptr) return FFTWPP_GPU_EINVAL;
+  *ptr=NULL;
+  if(bytes == 0) return 0;
+  CUDA_TRY(cudaMallocHost(ptr,bytes),"cudaMallocHost");
+  return 0;
+}
+
+int fftwpp_gpu_free_host(void *ptr)
+{
+  if(!ptr) return 0;
+  CUDA_TRY(cudaFreeHost(ptr),"cudaFreeHost");
+  return 0;
+}
+
+int fftwpp_gpu_memcpy_h2d(void *dst, const void *src, size_t bytes,
+                          void *stream)
+{
+  if(bytes == 0) return 0;
+  CUDA_TRY(cudaMemcpyAsync(dst,src,bytes,cudaMemcpyHostToDevice,
+                           (cudaStream_t) stream),"cudaMemcpyAsync(h2d)");
+  return 0;
+}
+
+int fftwpp_gpu_memcpy_d2h(void *dst, const void *src, size_t bytes,
+                          void *stream)
+{
+  if(bytes == 0) return 0;
+  CUDA_TRY(cudaMemcpyAsync(dst,src,bytes,cudaMemcpyDeviceToHost,
+                           (cudaStream_t) stream),"cudaMemcpyAsync(d2h)");
+  return 0;
+}
+
+int fftwpp_gpu_memcpy_d2d(void *dst, const void *src, size_t bytes,
+                          void *stream)
+{
+  if(bytes == 0) return 0;
+  CUDA_TRY(cudaMemcpyAsync(dst,src,bytes,cudaMemcpyDeviceToDevice,
+                           (cudaStream_t) stream),"cudaMemcpyAsync(d2d)");
+  return 0;
+}
+
+int fftwpp_gpu_memset(void *dst, int value, size_t bytes, void *stream)
+{
+  if(bytes == 0) return 0;
+  CUDA_TRY(cudaMemsetAsync(dst,value,bytes,(cudaStream_t) stream),
+           "cudaMemsetAsync");
+  return 0;
+}
+
+int fftwpp_gpu_memcpy2d(void *dst, size_t dpitch, const void *src,
+                        size_t spitch, size_t width, size_t height, int kind,
+                        void *stream)
+{
+  if(width == 0 || height == 0) return 0;
+  cudaMemcpyKind k=kind == 0 ? cudaMemcpyHostToDevice :
+    kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  CUDA_TRY(cudaMemcpy2DAsync(dst,dpitch,src,spitch,width,height,k,
+                             (cudaStream_t) stream),"cudaMemcpy2DAsync");
+  return 0;
+}
+
+int fftwpp_gpu_stream_sync(void *stream)
+{
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t) stream),
+           "cudaStreamSynchronize");
+  return 0;
+}
+
+int fftwpp_gpu_device_sync(void)
+{
+  CUDA_TRY(cudaDeviceSynchronize(),"cudaDeviceSynchronize");
+  return 0;
+}
+
+int fftwpp_gpu_is_device_ptr(const void *ptr)
+{
+  if(!ptr) return 0;
+  cudaPointerAttributes attr;
+  cudaError_t e=cudaPointerGetAttributes(&attr,ptr);
+  if(e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return attr.type == cudaMemoryTypeDevice ||
+    attr.type == cudaMemoryTypeManaged;
+}
+
+const char *fftwpp_gpu_last_error(void)
+{
+  return g_err;
+}
+
+uint64_t fftwpp_gpu_launch_count(void)
+{
+  return g_launches.load();
+}
+
+int fftwpp_gpu_plan_create(const fftwpp_gpu_pad_desc *desc,
+                           fftwpp_gpu_plan **plan)
+{
+  Plan *pl=NULL;
+  int rc=plan_build(desc,&pl);
+  if(rc) return rc;
+  *plan=(fftwpp_gpu_plan *) pl;
+  return 0;
+}
+
+int fftwpp_gpu_plan_destroy(fftwpp_gpu_plan *plan)
+{
+  Plan *pl=(Plan *) plan;
+  if(pl) {
+    fast_plan_free(pl);
+    delete pl;
+  }
+  return 0;
+}
+
+static int check_range(Plan *pl, uint64_t sb0, uint64_t nsb)
+{
+  if(!pl || nsb == 0 || sb0+nsb > pl->hsub.size()) {
+    set_error("invalid sub-block range [%llu,+%llu)",
+              (unsigned long long) sb0,(unsigned long long) nsb);
+    return FFTWPP_GPU_EINVAL;
+  }
+  return 0;
+}
+
+int fftwpp_gpu_forward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
+                       int all_layout, const void *f, void *F, uint64_t nrows,
+                       uint64_t f_rowstride, uint64_t F_rowstride,
+                       void *stream)
+{
+  Plan *pl=(Plan *) plan;
+  int rc=check_range(pl,sb0,nsb);
+  if(rc) return rc;
+  rc=fast_try_forward(pl,sb0,nsb,all_layout,f,F,nrows,f_rowstride,
+                      F_rowstride,(cudaStream_t) stream);
+  if(rc != 0) return rc < 0 ? rc : 0;
+  return generic_forward(pl,sb0,nsb,all_layout,f,F,nrows,f_rowstride,
+                         F_rowstride,(cudaStream_t) stream);
+}
+
+int fftwpp_gpu_backward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
+                        int all_layout, const void *F, void *f,
+                        int accumulate, double scale, uint64_t nrows,
+                        uint64_t F_rowstride, uint64_t f_rowstride,
+                        void *stream)
+{
+  Plan *pl=(Plan *) plan;
+  int rc=check_range(pl,sb0,nsb);
+  if(rc) return rc;
+  rc=fast_try_backward(pl,sb0,nsb,all_layout,F,f,accumulate,scale,nrows,
+                       F_rowstride,f_rowstride,(cudaStream_t) stream);
+  if(rc != 0) return rc < 0 ? rc : 0;
+  return generic_backward(pl,sb0,nsb,all_layout,F,f,accumulate,scale,nrows,
+                          F_rowstride,f_rowstride,(cudaStream_t) stream);
+}
+
+int fftwpp_gpu_convolve(fftwpp_gpu_plan *plan, void *const *f, uint32_t A,
+                        uint32_t B, int mult, double scale, uint64_t nrows,
+                        uint64_t rowstride, void *stream)
+{
+  Plan *pl=(Plan *) plan;
+  if(!pl || !f || A == 0 || B == 0 || A > MAXARRAYS || B > MAXARRAYS) {
+    set_error("convolve: invalid arguments");
+    return FFTWPP_GPU_EINVAL;
+  }
+  if((mult == FFTWPP_MULT_BINARY || mult == FFTWPP_MULT_REALBINARY ||
+      mult == FFTWPP_MULT_CORRELATION) && (A != 2 || B != 1)) {
+    set_error("convolve: binary multipliers need A=2, B=1");
+    return FFTWPP_GPU_EINVAL;
+  }
+  if(mult == FFTWPP_MULT_NONE && B > A) {
+    set_error("convolve: multNone needs B <= A");
+    return FFTWPP_GPU_EINVAL;
+  }
+  int rc=fast_try_convolve(pl,f,A,B,mult,scale,nrows,rowstride,
+                           (cudaStream_t) stream);
+  if(rc != 0) return rc < 0 ? rc : 0;
+  return generic_convolve(pl,f,A,B,mult,scale,nrows,rowstride,
+                          (cudaStream_t) stream);
+}
+
+int fftwpp_gpu_scale(double *x, double scale, uint64_t n0, uint64_t n1,
+                     uint64_t n2, uint64_t s0, uint64_t s1, void *stream)
+{
+  return launch_scale(x,scale,n0,n1,n2,s0,s1,(cudaStream_t) stream);
+}
+
+int fftwpp_gpu_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
+                     uint64_t n2, uint64_t d0, uint64_t d1, uint64_t s0,
+                     uint64_t s1, void *stream)
+{
+  return launch_copy3(dst,src,n0,n1,n2,d0,d1,s0,s1,(cudaStream_t) stream);
+}
+
+}

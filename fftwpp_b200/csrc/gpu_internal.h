@@ -1,0 +1,120 @@
+// gpu_internal.h -- shared declarations of the CUDA layer (not installed).
+#ifndef FFTWPP_GPU_INTERNAL_H
+#define FFTWPP_GPU_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/fftwpp_gpu.h"
+
+namespace fftwpp_gpu {
+
+static const int NTHREADS=256;
+static const int MAXRAD=24;    // stages of a mixed-radix plan
+static const int MAXPRIME=64;  // largest prime factor handled by the O(r^2) butterfly
+static const int MAXARRAYS=8;  // max(A,B) of a fused convolution
+
+// Roots of unity and radix schedule of one FFT length.
+struct FftTab {
+  const double2 *omega; // omega[k]=exp(2 pi i k/n)
+  int n;
+  int nrad;
+  int rad[MAXRAD];
+};
+
+struct SubBlockDev {
+  unsigned mlen;
+  unsigned nout;
+  unsigned flags;
+  unsigned tab;
+  long long k0;
+  long long off_call;
+  long long off_all;
+};
+
+// Everything a kernel needs about one padded FFT, passed by value.
+struct PlanDev {
+  int kind;
+  int Lin;          // stored input words per lane
+  int jmin, jmax;   // logical index range of the input
+  int C;
+  int zshift;       // <0: z1[e]; else z1[e>>zshift]*z2[e&mask]
+  long long N;
+  long long S;
+  const double2 *z1;
+  const double2 *z2;
+  FftTab tab[2];
+};
+
+struct ConvPtrs {
+  void *p[MAXARRAYS];
+};
+
+struct FastInfo; // fast_kernels.cu
+
+struct Plan {
+  fftwpp_gpu_pad_desc desc;
+  PlanDev dev;
+  std::vector<SubBlockDev> hsub;
+  const SubBlockDev *dsub;
+  unsigned mmax;
+  int device;
+  std::vector<void *> owned;
+  FastInfo *fast;
+  Plan() : dsub(NULL), mmax(0), device(0), fast(NULL) {}
+  ~Plan();
+};
+
+__host__ __device__ inline double wscale(double v, double s) {return v*s;}
+__host__ __device__ inline double2 wscale(double2 v, double s)
+{
+  return make_double2(v.x*s,v.y*s);
+}
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+int plan_build(const fftwpp_gpu_pad_desc *d, Plan **out);
+
+int generic_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                    const void *f, void *F, uint64_t nrows, uint64_t frs,
+                    uint64_t Frs, cudaStream_t st);
+int generic_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                     const void *F, void *f, int accumulate, double scale,
+                     uint64_t nrows, uint64_t Frs, uint64_t frs,
+                     cudaStream_t st);
+int generic_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
+                     int mult, double scale, uint64_t nrows, uint64_t rs,
+                     cudaStream_t st);
+int launch_scale(double *x, double scale, uint64_t n0, uint64_t n1,
+                 uint64_t n2, uint64_t s0, uint64_t s1, cudaStream_t st);
+int launch_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
+                 uint64_t n2, uint64_t d0, uint64_t d1, uint64_t s0,
+                 uint64_t s1, cudaStream_t st);
+
+// Specialised power-of-two kernels (fast_kernels.cu).  Each try_* returns
+// 1 if it handled the request, 0 if the generic kernel must be used, <0 on
+// error.
+void fast_plan_init(Plan *pl);
+void fast_plan_free(Plan *pl);
+int fast_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                     const void *f, void *F, uint64_t nrows, uint64_t frs,
+                     uint64_t Frs, cudaStream_t st);
+int fast_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                      const void *F, void *f, int accumulate, double scale,
+                      uint64_t nrows, uint64_t Frs, uint64_t frs,
+                      cudaStream_t st);
+int fast_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
+                      int mult, double scale, uint64_t nrows, uint64_t rs,
+                      cudaStream_t st);
+
+} // namespace fftwpp_gpu
+
+#endif

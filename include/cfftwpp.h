@@ -1,0 +1,139 @@
+/* cfftwpp.h -- C-callable API of lib_fftwpp.so (B200 build).
+ *
+ * Part 1 keeps the symbols that the reference's wrapper library actually
+ * defines (reference wrappers/cfftw++.cc:27-163; declarations
+ * wrappers/cfftw++.h), with the same argument meaning, so wrappers/fftwpp.py
+ * (ctypes), wrappers/fftwpp.f90 (bind(C)) and wrappers/cexample.c keep
+ * working against this library.  Arrays may be host pointers (staged) or
+ * device pointers (in place).  The *_dot/_dotf/_work prototypes of the
+ * reference header have no definitions in the reference either
+ *  and are not provided.
+ *
+ * Part 2 is a generic handle API over the same host classes
+ * (the fftPad family and Convolution, Convolution2, Convolution3) used by the parity tests, bench.py and the
+ * distributed driver: explicit (m,D,I), strides, real-data convolutions,
+ * residue-level forward/backward and the size/index queries that
+ * tests/hybrid*.cc walk.
+ */
+#ifndef CFFTWPP_B200_H
+#define CFFTWPP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#else
+#include <complex.h>
+#endif
+
+/* interleaved (re,im) doubles, layout-compatible with C99 double _Complex,
+ * std::complex<double> and the reference's Complex (Complex.h:29-38) */
+#ifdef __cplusplus
+typedef __complex__ double fftwpp_cplx;
+#else
+typedef double _Complex fftwpp_cplx;
+#endif
+
+/* ---------------- Part 1: reference wrapper API ---------------- */
+
+/* wrappers/cfftw++.cc:27-43 */
+double *create_doubleAlign(size_t n);
+void delete_doubleAlign(double *p);
+fftwpp_cplx *create_complexAlign(size_t n);
+void delete_complexAlign(fftwpp_cplx *p);
+
+/* wrappers/cfftw++.cc:45-52 */
+size_t get_fftwpp_maxthreads(void);
+void set_fftwpp_maxthreads(size_t nthreads);
+
+/* 1d complex, wrappers/cfftw++.cc:54-66 */
+typedef struct HybridConvolution HybridConvolution;
+HybridConvolution *fftwpp_create_conv1d(size_t L);
+void fftwpp_conv1d_delete(HybridConvolution *conv);
+void fftwpp_conv1d_convolve(HybridConvolution *conv, fftwpp_cplx *a,
+                            fftwpp_cplx *b);
+
+/* 1d Hermitian, wrappers/cfftw++.cc:68-86 */
+typedef struct HybridConvolutionHermitian HybridConvolutionHermitian;
+HybridConvolutionHermitian *fftwpp_create_hconv1d(size_t L);
+void fftwpp_hconv1d_delete(HybridConvolutionHermitian *conv);
+void fftwpp_HermitianSymmetrize(fftwpp_cplx *f);
+void fftwpp_hconv1d_convolve(HybridConvolutionHermitian *conv, fftwpp_cplx *a,
+                             fftwpp_cplx *b);
+
+/* 2d, wrappers/cfftw++.cc:88-124 */
+typedef struct HybridConvolution2 HybridConvolution2;
+HybridConvolution2 *fftwpp_create_conv2d(size_t Lx, size_t Ly);
+void fftwpp_conv2d_delete(HybridConvolution2 *conv);
+void fftwpp_HermitianSymmetrizeX(size_t Hx, size_t Hy, size_t x0,
+                                 fftwpp_cplx *f);
+void fftwpp_conv2d_convolve(HybridConvolution2 *conv, fftwpp_cplx *a,
+                            fftwpp_cplx *b);
+typedef struct HybridConvolutionHermitian2 HybridConvolutionHermitian2;
+HybridConvolutionHermitian2 *fftwpp_create_hconv2d(size_t Lx, size_t Ly);
+void fftwpp_hconv2d_delete(HybridConvolutionHermitian2 *conv);
+void fftwpp_hconv2d_convolve(HybridConvolutionHermitian2 *conv, fftwpp_cplx *a,
+                             fftwpp_cplx *b);
+
+/* 3d, wrappers/cfftw++.cc:126-163 */
+typedef struct HybridConvolution3 HybridConvolution3;
+HybridConvolution3 *fftwpp_create_conv3d(size_t Lx, size_t Ly, size_t Lz);
+void fftwpp_conv3d_delete(HybridConvolution3 *conv);
+void fftwpp_HermitianSymmetrizeXY(size_t Hx, size_t Hy, size_t Hz, size_t x0,
+                                  size_t y0, fftwpp_cplx *f);
+void fftwpp_conv3d_convolve(HybridConvolution3 *conv, fftwpp_cplx *a,
+                            fftwpp_cplx *b);
+typedef struct HybridConvolutionHermitian3 HybridConvolutionHermitian3;
+HybridConvolutionHermitian3 *fftwpp_create_hconv3d(size_t Lx, size_t Ly,
+                                                   size_t Lz);
+void fftwpp_hconv3d_delete(HybridConvolutionHermitian3 *conv);
+void fftwpp_hconv3d_convolve(HybridConvolutionHermitian3 *conv, fftwpp_cplx *a,
+                             fftwpp_cplx *b);
+
+/* ---------------- Part 2: generic handle API ---------------- */
+
+/* kind: 0 fftPad, 1 fftPadCentered, 2 fftPadHermitian, 3 fftPadReal
+ * (convolve.h:471,592,701,805).  m == 0: the chooser picks (m,D,I).
+ * mult: 0 multNone, 1 multBinary, 2 realMultBinary, 3 multcorrelation. */
+void *fftwpp_pad_create(int kind, size_t L, size_t M, size_t C, size_t S,
+                        size_t m, size_t D, long I, size_t A, size_t B,
+                        int mult);
+void fftwpp_pad_destroy(void *pad);
+/* out[0..31]: L,M,C,S,m,p,q,n,R,dr,D,D0,l,b,inplace,overwrite,centered,
+ * inputLength,wordSize,doubles,outputSize,workSizeW,workSizeV,nloops,loop2,
+ * conjugates,residueBlocks,paddedSize,normalization,repad,allRows,0 */
+void fftwpp_pad_info(void *pad, size_t *out);
+size_t fftwpp_pad_increment(void *pad, size_t r);
+size_t fftwpp_pad_blocksize(void *pad, size_t r);
+size_t fftwpp_pad_noutputs(void *pad, size_t r);
+size_t fftwpp_pad_span(void *pad, size_t r);
+size_t fftwpp_pad_index(void *pad, size_t r, size_t i);
+/* fft->forward(f,F,r) / fft->backward(F,f,r), host or device pointers */
+void fftwpp_pad_forward(void *pad, const double *f, double *F, size_t r);
+void fftwpp_pad_backward(void *pad, const double *F, double *f, size_t r);
+
+/* family: 0 complex, 1 centered Hermitian, 2 real (first dimension real).
+ * L,M,m,D,I: arrays of `dim` entries in x,y,z order; m[d]==0: chooser.
+ * Built like tests/hybridconv{,h,r}{,2,3}.cc build their objects. */
+void *fftwpp_conv_create(int dim, int family, const size_t *L, const size_t *M,
+                         const size_t *m, const size_t *D, const long *I,
+                         size_t Sx, size_t Sy, size_t A, size_t B, int mult);
+void fftwpp_conv_destroy(void *conv);
+/* out = {m,p,q,n,D,inplace,C,S} of dimension d */
+void fftwpp_conv_params(void *conv, int d, size_t *out);
+/* doubles per input array */
+size_t fftwpp_conv_doubles(void *conv);
+/* f: array of max(A,B) pointers (all host or all device).  normalized != 0:
+ * convolve(); else convolveRaw().  Result overwrites f[0..B). */
+void fftwpp_conv_convolve(void *conv, double **f, int normalized);
+/* batch size (x rows) of the y/z sweep of a 3-D convolution; 0 = all rows */
+void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk);
+
+/* stream used by every launch issued through this API (a cudaStream_t) */
+void fftwpp_set_stream(void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

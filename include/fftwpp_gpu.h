@@ -1,0 +1,169 @@
+/* fftwpp_gpu.h -- thin C ABI between the host C++ classes (convolve.h mirror)
+ * and the hand-written sm_100a CUDA kernels.  Plain pointers and sizes only;
+ * no CUDA, torch or C++ types in any signature, so the host layer (and any
+ * FFI: ctypes, Fortran bind(C), cgo) compiles without nvcc.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   fftwpp_gpu_plan_create     fftPad*::init(): FFTW plans + Zetaqm/ZetaqmS/
+ *                              Zetaqp tables   convolve.cc:511-719,1967-2004,
+ *                                              4309-4421,5449-5637,126-140
+ *   fftwpp_gpu_forward         (fft->*Forward)(f,F,r,W): pre-twiddle/pad loop
+ *                              + fftm->fft     convolve.cc:771-1466 (fftPad),
+ *                              2006-3550 (Centered), 4439-5200 (Hermitian),
+ *                              5726-6600 (Real); fftw++.h:313,827-896
+ *   fftwpp_gpu_backward        (fft->*Backward)(F,f,r,W): ifftm->fft +
+ *                              post-twiddle accumulate  convolve.cc:1468-1965,
+ *                              2038-4307, 4484-5447, 6602-7483
+ *   fftwpp_gpu_convolve        Convolution::convolveRaw residue loop with the
+ *                              multiplier fused  convolve.cc:7513-7575,
+ *                              convolve.h:1114-1149; multipliers
+ *                              convolve.cc:26-110
+ *   fftwpp_gpu_scale           Convolution{,2,3}::normalize
+ *                              convolve.h:1105-1112,1459-1471,1791-1808
+ *   fftwpp_gpu_hermitian_*     HermitianSymmetrize{,X,XY} convolve.h:1168-1267
+ *   fftwpp_gpu_pack/unpack +   mpitranspose<Complex>::localize0/1
+ *   fftwpp_gpu_comm_*          mpi/mpitranspose.h:632-931 (NCCL all-to-all)
+ *
+ * All functions return 0 on success or a negative FFTWPP_GPU_E* code; the C++
+ * layer turns failures into the reference's "message on cerr + exit" policy
+ * (convolve.h:226-232).  There is NO CPU fallback: without a CUDA device the
+ * compute entry points return FFTWPP_GPU_ENODEVICE.
+ */
+#ifndef FFTWPP_GPU_H
+#define FFTWPP_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFTWPP_GPU_OK          0
+#define FFTWPP_GPU_ENODEVICE  -1
+#define FFTWPP_GPU_EINVAL     -2
+#define FFTWPP_GPU_ENOMEM     -3
+#define FFTWPP_GPU_ECUDA      -4
+#define FFTWPP_GPU_EUNSUPPORTED -5
+#define FFTWPP_GPU_ENCCL      -6
+
+/* Kinds of padded FFT (reference classes, convolve.h:471,592,701,805). */
+#define FFTWPP_KIND_COMPLEX   0  /* fftPad          */
+#define FFTWPP_KIND_CENTERED  1  /* fftPadCentered  */
+#define FFTWPP_KIND_HERMITIAN 2  /* fftPadHermitian */
+#define FFTWPP_KIND_REAL      3  /* fftPadReal      */
+
+/* Multipliers fused into fftwpp_gpu_convolve (convolve.cc:26-110). */
+#define FFTWPP_MULT_NONE        0
+#define FFTWPP_MULT_BINARY      1
+#define FFTWPP_MULT_REALBINARY  2
+#define FFTWPP_MULT_CORRELATION 3
+
+/* Sub-block flags. */
+#define FFTWPP_SB_CONJ_OUT 1u  /* store conj(FFT): r2c (sign -1) convention of
+                                  the r=0 block of fftPadReal */
+
+/* One FFT sub-block of a residue pass.  The forward pass computes
+ *   W[s] = sum_{j in [jmin,jmax), j = s (mod mlen)} zeta_N^{k0*j} * g(j)
+ *   out[l] = sum_s zeta_mlen^{l*s} W[s],  l in [0,nout)
+ * where g is the logical (origin-shifted / Hermitian-extended / real) input,
+ * and stores out[l] at word offset off_* + S_out*l + c of the output buffer.
+ * off_call is the reference's own layout for a single forward(r) call
+ * (block d at b*d, convolve.h:297-326,956-979); off_all is the layout when
+ * every residue is produced by one launch (all blocks concatenated).
+ * Offsets are in output words (Complex, or double for Hermitian). */
+typedef struct {
+  uint32_t mlen;
+  uint32_t nout;
+  uint32_t flags;
+  uint32_t reserved;
+  uint64_t k0;
+  uint64_t off_call;
+  uint64_t off_all;
+} fftwpp_gpu_subblock;
+
+typedef struct {
+  int32_t kind;      /* FFTWPP_KIND_*                                     */
+  int32_t reserved;
+  uint64_t L;        /* reference L (logical unpadded length)             */
+  uint64_t Lin;      /* stored input words per column (inputLength())     */
+  uint64_t N;        /* padded length m*q                                 */
+  uint64_t m;        /* inner FFT length                                  */
+  uint64_t C;        /* number of interleaved columns                     */
+  uint64_t S;        /* stride between successive elements (words)        */
+  uint64_t nsub;     /* number of sub-blocks                              */
+  const fftwpp_gpu_subblock *sub; /* host array [nsub]                    */
+} fftwpp_gpu_pad_desc;
+
+typedef struct fftwpp_gpu_plan fftwpp_gpu_plan;
+
+/* ---- device / memory / stream plumbing ---- */
+int fftwpp_gpu_device_count(void);
+int fftwpp_gpu_set_device(int device);
+int fftwpp_gpu_malloc(void **ptr, size_t bytes);
+int fftwpp_gpu_free(void *ptr);
+int fftwpp_gpu_malloc_host(void **ptr, size_t bytes);   /* pinned */
+int fftwpp_gpu_free_host(void *ptr);
+int fftwpp_gpu_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int fftwpp_gpu_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int fftwpp_gpu_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int fftwpp_gpu_memset(void *dst, int value, size_t bytes, void *stream);
+/* strided 2-D copies (rows of `width` bytes) */
+int fftwpp_gpu_memcpy2d(void *dst, size_t dpitch, const void *src, size_t spitch,
+                        size_t width, size_t height, int kind /*0 h2d,1 d2h,2 d2d*/,
+                        void *stream);
+int fftwpp_gpu_stream_sync(void *stream);
+int fftwpp_gpu_device_sync(void);
+/* 1 if ptr is device (or managed) memory, 0 if host, <0 on error */
+int fftwpp_gpu_is_device_ptr(const void *ptr);
+const char *fftwpp_gpu_last_error(void);
+/* number of kernels launched by this library since load (bench bookkeeping) */
+uint64_t fftwpp_gpu_launch_count(void);
+
+/* ---- plans ---- */
+int fftwpp_gpu_plan_create(const fftwpp_gpu_pad_desc *desc, fftwpp_gpu_plan **plan);
+int fftwpp_gpu_plan_destroy(fftwpp_gpu_plan *plan);
+
+/* Forward residue pass over sub-blocks [sb0, sb0+nsb) for `nrows` independent
+ * rows.  f: input words (Complex, or double for FFTWPP_KIND_REAL); F: output
+ * words.  Row r reads f + r*f_rowstride and writes F + r*F_rowstride (strides
+ * in words of the respective arrays).  all_layout selects off_all/off_call. */
+int fftwpp_gpu_forward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
+                       int all_layout, const void *f, void *F,
+                       uint64_t nrows, uint64_t f_rowstride,
+                       uint64_t F_rowstride, void *stream);
+
+/* Backward (adjoint) pass: f (=|+=) scale * sum over the given sub-blocks.
+ * accumulate != 0 adds to the existing contents of f. */
+int fftwpp_gpu_backward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
+                        int all_layout, const void *F, void *f,
+                        int accumulate, double scale,
+                        uint64_t nrows, uint64_t F_rowstride,
+                        uint64_t f_rowstride, void *stream);
+
+/* Fused 1-D convolution of nrows independent rows (plan must have C==1):
+ * for every sub-block, forward all A inputs, apply the multiplier, backward
+ * the B outputs and accumulate; padded data never leaves the SM.  The result
+ * times `scale` overwrites f[0..B).  f: array of max(A,B) device pointers
+ * (host array of pointers). */
+int fftwpp_gpu_convolve(fftwpp_gpu_plan *plan, void *const *f, uint32_t A,
+                        uint32_t B, int mult, double scale, uint64_t nrows,
+                        uint64_t rowstride, void *stream);
+
+/* x[i] *= scale over a (n0 x n1 x n2) box of doubles with strides s0,s1 (in
+ * doubles) and unit stride in the last dimension. */
+int fftwpp_gpu_scale(double *x, double scale, uint64_t n0, uint64_t n1,
+                     uint64_t n2, uint64_t s0, uint64_t s1, void *stream);
+
+/* Pack/unpack for the distributed transpose (mpi/mpitranspose.h:632-931):
+ * copies an (n0 x n1 x n2)-word box between two strided layouts
+ * (16-byte words). dst[i*d0+j*d1+k] = src[i*s0+j*s1+k]. */
+int fftwpp_gpu_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
+                     uint64_t n2, uint64_t d0, uint64_t d1, uint64_t s0,
+                     uint64_t s1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,158 @@
+"""GPU parity of Convolution / Convolution2 / Convolution3 against the oracle
+(numpy explicit-padding FFT convolution, itself pinned to the reference in
+tests/test_oracle.py), through the C ABI with host buffers.
+Mirrors the reference's `-E` accuracy runs (tests/hybridconv*.cc with the
+deterministic ramps) and tests/tests.py:561-653 parameter sweeps."""
+import itertools
+
+import numpy as np
+import pytest
+
+import fftwpp_b200 as fp
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def crand(rng, *shape):
+    return rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)
+
+
+def check(fam, L, M, m=None, D=None, I=None, mult=None, seed=0):
+    rng = np.random.default_rng(1234 + seed)
+    L = list(L)
+    if fam == fp.FAMILY_COMPLEX:
+        f, g = crand(rng, *L), crand(rng, *L)
+        want = O.correlation_complex(f, g) if mult == fp.MULT_CORRELATION else O.conv_complex(f, g)
+    elif fam == fp.FAMILY_REAL:
+        f, g = rng.uniform(-1, 1, L), rng.uniform(-1, 1, L)
+        want = O.conv_real(f, g)
+    else:
+        shp = L[:-1] + [(L[-1] + 1) // 2]
+        f, g = crand(rng, *shp), crand(rng, *shp)
+        O.symmetrize(L, f)
+        O.symmetrize(L, g)
+        want = O.conv_hermitian(L, f, g)
+    conv = fp.HybridConv(L, M, family=fam, m=m, D=D, I=I, mult=mult)
+    a = [np.ascontiguousarray(f.copy()), np.ascontiguousarray(g.copy())]
+    conv.convolve(a)
+    padded = [conv.params(d)["m"] * conv.params(d)["q"] for d in range(len(L))]
+    err = O.rel_l2(a[0], want)
+    assert err < O.tolerance(*padded), (err, [conv.params(d) for d in range(len(L))])
+    conv.close()
+    return err
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 5, 7, 8, 16, 31, 64, 100, 512, 1000])
+def test_conv1d_complex_auto(L):
+    check(fp.FAMILY_COMPLEX, [L], [2 * L], seed=L)
+
+
+def _forced_1d(kind_family):
+    out = []
+    centered = kind_family == fp.FAMILY_HERMITIAN
+    for L in (3, 5, 7, 8, 12, 16):
+        Ms = [2 * L, 5 * L // 2, 3 * L] if not centered else [(3 * L + 1) // 2, 2 * L, 3 * L]
+        for M in Ms:
+            for m in sorted(set([M, L + 1, L, (L + 1) // 2, max(2, L // 4)])):
+                p, n, q = O.parameters(L, M, m, centered)
+                if q * m < M:
+                    continue
+                if kind_family == fp.FAMILY_COMPLEX:
+                    Ds = [1] + ([n] if n > 1 else []) + ([2] if n > 2 else [])
+                    if q == 1:
+                        Ds = [1]
+                elif kind_family == fp.FAMILY_HERMITIAN:
+                    if q == 1:
+                        Ds = [1]
+                    elif p == 2:
+                        Ds = [2]
+                    else:
+                        continue
+                else:
+                    if q > 1 and p > 2:
+                        continue
+                    if not ((n % 2 == 1 or p <= 2) and (q % 2 == 1 or m % 2 == 0)):
+                        continue
+                    Ds = [1]
+                    if (n - 1) // 2 > 1:
+                        Ds.append((n - 1) // 2)
+                for D in Ds:
+                    out.append((L, M, m, D))
+    return out
+
+
+@pytest.mark.parametrize("L,M,m,D", _forced_1d(fp.FAMILY_COMPLEX))
+def test_conv1d_complex_forced(L, M, m, D):
+    check(fp.FAMILY_COMPLEX, [L], [M], m=[m], D=[D], I=[0], seed=L + M + m)
+
+
+@pytest.mark.parametrize("L,M,m,D", _forced_1d(fp.FAMILY_HERMITIAN))
+def test_conv1d_hermitian_forced(L, M, m, D):
+    check(fp.FAMILY_HERMITIAN, [L], [M], m=[m], D=[D], I=[0], seed=L + M + m)
+
+
+@pytest.mark.parametrize("L,M,m,D", _forced_1d(fp.FAMILY_REAL))
+def test_conv1d_real_forced(L, M, m, D):
+    check(fp.FAMILY_REAL, [L], [M], m=[m], D=[D], I=[0], seed=L + M + m)
+
+
+@pytest.mark.parametrize("L", [4, 7, 8, 33, 256])
+def test_conv1d_hermitian_auto(L):
+    check(fp.FAMILY_HERMITIAN, [L], None, seed=L)
+
+
+@pytest.mark.parametrize("L", [4, 7, 8, 33, 256, 1024])
+def test_conv1d_real_auto(L):
+    check(fp.FAMILY_REAL, [L], [2 * L], seed=L)
+
+
+def test_conv1d_correlation():
+    check(fp.FAMILY_COMPLEX, [24], [48], mult=fp.MULT_CORRELATION)
+
+
+@pytest.mark.parametrize("fam", [fp.FAMILY_COMPLEX, fp.FAMILY_REAL, fp.FAMILY_HERMITIAN])
+@pytest.mark.parametrize("L", [(4, 4), (5, 7), (8, 6), (16, 16), (33, 20), (64, 128)])
+def test_conv2d(fam, L):
+    M = None if fam == fp.FAMILY_HERMITIAN else [2 * l for l in L]
+    check(fam, L, M, seed=sum(L))
+
+
+@pytest.mark.parametrize("fam", [fp.FAMILY_COMPLEX, fp.FAMILY_REAL, fp.FAMILY_HERMITIAN])
+@pytest.mark.parametrize("L", [(4, 4, 4), (3, 5, 7), (8, 6, 5), (16, 16, 16), (12, 9, 20)])
+def test_conv3d(fam, L):
+    M = None if fam == fp.FAMILY_HERMITIAN else [2 * l for l in L]
+    check(fam, L, M, seed=sum(L))
+
+
+@pytest.mark.parametrize("fam", [fp.FAMILY_COMPLEX, fp.FAMILY_REAL])
+def test_conv3d_forced_hybrid(fam):
+    # explicit m per dimension: p=1 / p=2 / explicit mixes
+    check(fam, (8, 8, 8), (16, 16, 16), m=[8, 4, 16], D=[1, 1, 1], I=[0, 0, 0])
+    check(fam, (6, 10, 12), (12, 20, 24), m=[6, 5, 12], D=[1, 1, 1], I=[0, 0, 0])
+
+
+def test_reference_ramp_3d_real():
+    # the reference's own deterministic input (tests/hybridconvr3.cc:54-64)
+    Lx = Ly = Lz = 4
+    i, j, k = np.meshgrid(np.arange(Lx), np.arange(Ly), np.arange(Lz), indexing="ij")
+    f = [(i + (a + 1) * j + a * k + 1).astype(np.float64) for a in range(2)]
+    want = O.direct("real", f[0], f[1])
+    conv = fp.HybridConv([Lx, Ly, Lz], [8, 8, 8], family=fp.FAMILY_REAL)
+    a = [np.ascontiguousarray(f[0].copy()), np.ascontiguousarray(f[1].copy())]
+    conv.convolve(a)
+    assert O.rel_l2(a[0], want) < 1e-12
+
+
+def test_wrapper_api_matches_generic():
+    # reference wrapper entry points (wrappers/cfftw++.cc:54-66)
+    import ctypes
+    L = 37
+    rng = np.random.default_rng(5)
+    f, g = crand(rng, L), crand(rng, L)
+    want = O.conv_complex(f, g)
+    h = fp.lib.fftwpp_create_conv1d(L)
+    a, b = f.copy(), g.copy()
+    fp.lib.fftwpp_conv1d_convolve(h, a.ctypes.data, b.ctypes.data)
+    fp.lib.fftwpp_conv1d_delete(h)
+    assert O.rel_l2(a, want) < 1e-12
