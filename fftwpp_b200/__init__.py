@@ -11,4 +11,5 @@ from .api import (  # noqa: F401
     Pad, HybridConv, KIND_COMPLEX, KIND_CENTERED, KIND_HERMITIAN, KIND_REAL,
     MULT_NONE, MULT_BINARY, MULT_REALBINARY, MULT_CORRELATION,
     FAMILY_COMPLEX, FAMILY_HERMITIAN, FAMILY_REAL, launch_count, set_stream,
+    profile_enable, profile_read, pinned_array,
 )

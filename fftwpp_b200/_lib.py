@@ -78,3 +78,7 @@ _sig("fftwpp_gpu_launch_count", c_u64)
 _sig("fftwpp_gpu_last_error", ctypes.c_char_p)
 _sig("fftwpp_gpu_device_sync", c_int)
 _sig("fftwpp_gpu_set_device", c_int, c_int)
+_sig("fftwpp_gpu_profile_enable", c_int, c_int)
+_sig("fftwpp_gpu_profile_read", c_int, P(c_double), P(c_u64))
+_sig("fftwpp_gpu_malloc_host", c_int, P(c_void_p), c_size_t)
+_sig("fftwpp_gpu_free_host", c_int, c_void_p)

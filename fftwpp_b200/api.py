@@ -160,3 +160,39 @@ class HybridConv:
         ptrs = (ctypes.c_void_p * n)(*[_ptr(a) for a in arrays[:n]])
         lib.fftwpp_conv_convolve(self._h, ptrs, 1 if normalized else 0)
         return arrays[0] if self.B == 1 else arrays[:self.B]
+
+
+PROFILE_OPS = ("forward", "backward", "convolve", "other")
+PROFILE_PASSES = {0: "-", 1: "x", 2: "y", 3: "z"}
+
+
+def profile_enable(on=True):
+    """Bracket every launch of the library with CUDA events on its stream."""
+    lib.fftwpp_gpu_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{(pass, op): (total_ms, launches)} since profile_enable(True)."""
+    ms = (ctypes.c_double * 64)()
+    cnt = (ctypes.c_uint64 * 64)()
+    rc = lib.fftwpp_gpu_profile_read(ms, cnt)
+    if rc:
+        raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+    out = {}
+    for k in range(64):
+        if cnt[k]:
+            out[(PROFILE_PASSES.get(k // 4, str(k // 4)), PROFILE_OPS[k % 4])] = (
+                float(ms[k]), int(cnt[k]))
+    return out
+
+
+def pinned_array(shape, dtype):
+    """numpy array backed by page-locked host memory (for the e2e timing)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    rc = lib.fftwpp_gpu_malloc_host(ctypes.byref(p), n)
+    if rc:
+        raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+    buf = (ctypes.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr

@@ -215,7 +215,7 @@ fftBase::fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
   ThreadBase(app.threads), L(L), M(M), C(C), S(S == 0 ? C : S), m(0), p(0),
   q(0), n(0), R(0), dr(0), D(0), D0(0), Cm(0), Sm(0), l(0), b(0),
   inplace(false), app(app), centered(centered), overwrite(false),
-  gpuplan(NULL), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL)
+  gpuplan(NULL), gputag(0), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL)
 {
   checkParameters();
 }
@@ -225,7 +225,7 @@ fftBase::fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
   ThreadBase(app.threads), L(L), M(M), C(C), S(S == 0 ? C : S), m(m), p(0),
   q(0), n(0), R(0), dr(0), D(D), D0(0), Cm(0), Sm(0), l(0), b(0),
   inplace(inplace), app(app), centered(centered), overwrite(false),
-  gpuplan(NULL), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL)
+  gpuplan(NULL), gputag(0), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL)
 {
   checkParameters();
   this->app.D=D;
@@ -453,7 +453,14 @@ fftwpp_gpu_plan *fftBase::plan()
   d.nsub=s.size();
   d.sub=s.data();
   gpu::check(fftwpp_gpu_plan_create(&d,&gpuplan),"plan creation");
+  fftwpp_gpu_plan_set_tag(gpuplan,gputag);
   return gpuplan;
+}
+
+void fftBase::setTag(int tag)
+{
+  gputag=tag;
+  if(gpuplan) fftwpp_gpu_plan_set_tag(gpuplan,gputag);
 }
 
 // Host-pointer staging for forward()/backward().
@@ -887,6 +894,7 @@ Convolution::Convolution(fftBase *fft, Complex **, Complex *, Complex *) :
   indices.copy(NULL,0);
   indices.fft=fft;
   scale=1.0/normalization();
+  if(fft->tag() == 0) fft->setTag(1);
   multId=multiplierId(mult);
   if(fft->C != 1 && multId != FFTWPP_MULT_NONE) {
     // as in the reference the multiplier only sees C == 1 data
@@ -1102,6 +1110,8 @@ Convolution2::Convolution2(fftBase *fftx, fftBase *ffty, Complex **,
   threads=1;
   convolvey=new Convolution*[1];
   convolvey[0]=new Convolution(ffty);
+  fftx->setTag(1);
+  ffty->setTag(2);
   Lx=fftx->L;
   Ly=fftx->C;
   Sx=fftx->S;
@@ -1209,6 +1219,9 @@ Convolution3::Convolution3(fftBase *fftx, fftBase *ffty, fftBase *fftz,
   convolvez=NULL;
   convolveyz=new Convolution2*[1];
   convolveyz[0]=mpi ? NULL : new Convolution2(ffty,fftz);
+  fftx->setTag(1);
+  ffty->setTag(2);
+  fftz->setTag(3);
   Lx=fftx->L;
   Ly=ffty->L;
   Lz=ffty->C;

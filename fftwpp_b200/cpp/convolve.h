@@ -238,6 +238,9 @@ public:
   // The GPU plan is created on first use so that the bookkeeping above can be
   // queried (and tested) on a host without a CUDA device.
   fftwpp_gpu_plan *plan();
+  // Profiling tag of this pass (1 = x, 2 = y, 3 = z), see fftwpp_gpu_profile_*.
+  void setTag(int tag);
+  int tag() {return gputag;}
   const std::vector<ResidueCall>& calls() {return callTable;}
   // Rows (FFT outputs per column) when all residues are produced at once.
   size_t allRows() {return totalRows;}
@@ -247,6 +250,7 @@ public:
 
 protected:
   fftwpp_gpu_plan *gpuplan;
+  int gputag;
   std::vector<struct SubBlockHost> *subHost;
   std::vector<ResidueCall> callTable;
   size_t totalRows;

@@ -155,6 +155,21 @@ int fftwpp_gpu_plan_create(const fftwpp_gpu_pad_desc *desc,
   return 0;
 }
 
+int fftwpp_gpu_plan_set_tag(fftwpp_gpu_plan *plan, int tag)
+{
+  if(!plan || tag < 0 || tag >= PROF_KEYS/4) return FFTWPP_GPU_EINVAL;
+  ((Plan *) plan)->tag=tag;
+  return 0;
+}
+
+int fftwpp_gpu_profile_enable(int on) {return prof_enable(on);}
+
+int fftwpp_gpu_profile_read(double *ms, uint64_t *count)
+{
+  if(!ms || !count) return FFTWPP_GPU_EINVAL;
+  return prof_read(ms,count);
+}
+
 int fftwpp_gpu_plan_destroy(fftwpp_gpu_plan *plan)
 {
   Plan *pl=(Plan *) plan;

@@ -808,11 +808,66 @@ static int choose_tile(const Plan *pl, size_t narr_in, size_t narr_w,
   return 0;
 }
 
-static int check_launch(const char *what)
+// ---- optional profiling: one event pair per launch, summed per key ----
+struct ProfRec {int key; cudaEvent_t e0, e1;};
+static bool g_prof=false;
+static std::vector<ProfRec> g_prof_recs;
+static int g_prof_open=-1;
+static std::mutex g_prof_mu;
+
+void prof_begin(int key, cudaStream_t st)
+{
+  if(!g_prof) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  ProfRec r;
+  r.key=key;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0,st);
+  g_prof_recs.push_back(r);
+  g_prof_open=(int) g_prof_recs.size()-1;
+}
+
+int check_launch(const char *what, cudaStream_t st)
 {
   cudaError_t e=cudaGetLastError();
+  if(g_prof && g_prof_open >= 0) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    cudaEventRecord(g_prof_recs[g_prof_open].e1,st);
+    g_prof_open=-1;
+  }
   if(e != cudaSuccess) return cuda_fail(e,what);
   g_launches.fetch_add(1);
+  return 0;
+}
+
+int prof_enable(int on)
+{
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for(size_t i=0; i < g_prof_recs.size(); ++i) {
+    cudaEventDestroy(g_prof_recs[i].e0);
+    cudaEventDestroy(g_prof_recs[i].e1);
+  }
+  g_prof_recs.clear();
+  g_prof_open=-1;
+  g_prof=on != 0;
+  return 0;
+}
+
+int prof_read(double *ms, uint64_t *count)
+{
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for(int k=0; k < PROF_KEYS; ++k) {ms[k]=0.0; count[k]=0;}
+  cudaError_t e=cudaDeviceSynchronize();
+  if(e != cudaSuccess) return cuda_fail(e,"cudaDeviceSynchronize");
+  for(size_t i=0; i < g_prof_recs.size(); ++i) {
+    float t=0.0f;
+    if(cudaEventElapsedTime(&t,g_prof_recs[i].e0,g_prof_recs[i].e1) == cudaSuccess) {
+      int k=g_prof_recs[i].key & (PROF_KEYS-1);
+      ms[k] += t;
+      ++count[k];
+    }
+  }
   return 0;
 }
 
@@ -844,10 +899,11 @@ int generic_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   DISPATCH_KIND(pl->dev.kind,
     rc=enable_smem(forward_kernel<K>);
     if(rc) return rc;
+    prof_begin(4*pl->tag+0,st);
     forward_kernel<K><<<(unsigned) grid,NTHREADS,smem,st>>>
       (pl->dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,
        (long long) frs,(long long) Frs,TR,TC,ntc,inbytes));
-  return check_launch("forward_kernel");
+  return check_launch("forward_kernel",st);
 }
 
 int generic_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
@@ -871,10 +927,11 @@ int generic_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   DISPATCH_KIND(pl->dev.kind,
     rc=enable_smem(backward_kernel<K>);
     if(rc) return rc;
+    prof_begin(4*pl->tag+1,st);
     backward_kernel<K><<<(unsigned) grid,NTHREADS,smem,st>>>
       (pl->dev,pl->dsub+sb0,(int) nsb,layout,F,f,accumulate,scale,
        (long long) nrows,(long long) Frs,(long long) frs,TR,TC,ntc,accbytes));
-  return check_launch("backward_kernel");
+  return check_launch("backward_kernel",st);
 }
 
 int generic_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
@@ -903,10 +960,11 @@ int generic_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
   DISPATCH_KIND(pl->dev.kind,
     rc=enable_smem(convolve_kernel<K>);
     if(rc) return rc;
+    prof_begin(4*pl->tag+2,st);
     convolve_kernel<K><<<(unsigned) grid,NTHREADS,smem,st>>>
       (pl->dev,pl->dsub,(int) pl->hsub.size(),ptrs,(int) A,(int) B,mult,
        scale,(long long) nrows,(long long) rs,TR,inbytes,wstride));
-  return check_launch("convolve_kernel");
+  return check_launch("convolve_kernel",st);
 }
 
 int launch_scale(double *x, double scale, uint64_t n0, uint64_t n1,
@@ -915,8 +973,9 @@ int launch_scale(double *x, double scale, uint64_t n0, uint64_t n1,
   uint64_t total=n0*n1*n2;
   if(total == 0) return 0;
   unsigned grid=(unsigned) std::min<uint64_t>((total+255)/256,148*16);
+  prof_begin(3,st);
   scale_kernel<<<grid,256,0,st>>>(x,scale,n0,n1,n2,s0,s1);
-  return check_launch("scale_kernel");
+  return check_launch("scale_kernel",st);
 }
 
 int launch_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
@@ -926,9 +985,10 @@ int launch_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
   uint64_t total=n0*n1*n2;
   if(total == 0) return 0;
   unsigned grid=(unsigned) std::min<uint64_t>((total+255)/256,148*16);
+  prof_begin(3,st);
   copy3_kernel<<<grid,256,0,st>>>((double2 *) dst,(const double2 *) src,
                                    n0,n1,n2,d0,d1,s0,s1);
-  return check_launch("copy3_kernel");
+  return check_launch("copy3_kernel",st);
 }
 
 } // namespace fftwpp_gpu

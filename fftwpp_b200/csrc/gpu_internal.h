@@ -66,7 +66,8 @@ struct Plan {
   int device;
   std::vector<void *> owned;
   FastInfo *fast;
-  Plan() : dsub(NULL), mmax(0), device(0), fast(NULL) {}
+  int tag; // profiling tag set by the host layer (which pass this plan serves)
+  Plan() : dsub(NULL), mmax(0), device(0), fast(NULL), tag(0) {}
   ~Plan();
 };
 
@@ -82,6 +83,14 @@ void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 
 int plan_build(const fftwpp_gpu_pad_desc *d, Plan **out);
+
+// Optional per-launch CUDA-event timing (fftwpp_gpu_profile_*).  key =
+// 4*plan tag + op, op: 0 forward, 1 backward, 2 fused convolution, 3 other.
+static const int PROF_KEYS=64;
+void prof_begin(int key, cudaStream_t st);
+int check_launch(const char *what, cudaStream_t st);
+int prof_enable(int on);
+int prof_read(double *ms, uint64_t *count);
 
 int generic_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                     const void *f, void *F, uint64_t nrows, uint64_t frs,

@@ -124,6 +124,16 @@ uint64_t fftwpp_gpu_launch_count(void);
 int fftwpp_gpu_plan_create(const fftwpp_gpu_pad_desc *desc, fftwpp_gpu_plan **plan);
 int fftwpp_gpu_plan_destroy(fftwpp_gpu_plan *plan);
 
+/* ---- optional per-launch timing with CUDA events on the launch stream ----
+ * Plans carry a small tag (0..15) naming the pass they serve (the host classes
+ * use 1 = x, 2 = y, 3 = z).  While profiling is enabled every launch is
+ * bracketed by an event pair; profile_read synchronises the device and returns,
+ * for key = 4*tag + op (op 0 forward, 1 backward, 2 fused convolution, 3
+ * other), the summed milliseconds and the number of launches (arrays of 64). */
+int fftwpp_gpu_plan_set_tag(fftwpp_gpu_plan *plan, int tag);
+int fftwpp_gpu_profile_enable(int on);
+int fftwpp_gpu_profile_read(double *ms, uint64_t *count);
+
 /* Forward residue pass over sub-blocks [sb0, sb0+nsb) for `nrows` independent
  * rows.  f: input words (Complex, or double for FFTWPP_KIND_REAL); F: output
  * words.  Row r reads f + r*f_rowstride and writes F + r*F_rowstride (strides
