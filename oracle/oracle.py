@@ -154,7 +154,8 @@ def conv_complex(f, g):
     f = np.asarray(f, dtype=np.complex128)
     g = np.asarray(g, dtype=np.complex128)
     shape = [2 * n - 1 for n in f.shape]
-    h = np.fft.ifftn(np.fft.fftn(f, shape) * np.fft.fftn(g, shape))
+    ax = list(range(f.ndim))
+    h = np.fft.ifftn(np.fft.fftn(f, shape, axes=ax) * np.fft.fftn(g, shape, axes=ax), axes=ax)
     return np.ascontiguousarray(h[tuple(slice(0, n) for n in f.shape)])
 
 
@@ -173,13 +174,16 @@ def conv_real(f, g):
     f = np.asarray(f, dtype=np.float64)
     g = np.asarray(g, dtype=np.float64)
     shape = [2 * n - 1 for n in f.shape]
-    h = np.fft.irfftn(np.fft.rfftn(f, shape) * np.fft.rfftn(g, shape), shape)
+    ax = list(range(f.ndim))
+    h = np.fft.irfftn(np.fft.rfftn(f, shape, axes=ax) * np.fft.rfftn(g, shape, axes=ax),
+                      shape, axes=ax)
     return np.ascontiguousarray(h[tuple(slice(0, n) for n in f.shape)])
 
 
 def _full_conv(a, b):
     shape = [x + y - 1 for x, y in zip(a.shape, b.shape)]
-    return np.fft.ifftn(np.fft.fftn(a, shape) * np.fft.fftn(b, shape))
+    ax = list(range(a.ndim))
+    return np.fft.ifftn(np.fft.fftn(a, shape, axes=ax) * np.fft.fftn(b, shape, axes=ax), axes=ax)
 
 
 def conv_centered1(f, g):
