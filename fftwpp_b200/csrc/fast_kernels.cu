@@ -1,31 +1,917 @@
-// fast_kernels.cu -- specialised power-of-two register kernels (hot shapes).
+// fast_kernels.cu -- specialised sm_100a kernels for power-of-two residue
+// passes (the shapes of every BASELINE config).  Same mathematics and same
+// C ABI as the generic kernels in gpu_core.cu; what changes is the execution:
+//
+//  * every thread owns 8 complex points in registers; an FFT of length
+//    N = 2^k is a sequence of register radix-8 butterflies (plus one radix-2/4
+//    pass when 3 does not divide k) with shared-memory exchanges in between --
+//    decimation in frequency forward (digit-reversed result), exact adjoint
+//    backward, so the fused convolution multiplies in scrambled order and never
+//    reorders;
+//  * implicit zero padding, residue twiddles, the multiplier and the
+//    conjugate-twiddle accumulation over residues all happen in registers: the
+//    padded data never exists in HBM and the accumulators of the fused
+//    convolution never leave the register file;
+//  * strided ("Many") passes take tiles of T adjacent columns so that every
+//    global access is a run of T*16 contiguous bytes, and keep the tile
+//    lane-fastest in shared memory (bank-conflict free for every stage);
+//    contiguous rows use a padded per-row exchange buffer (index p + p/8)
+//    and per-row named barriers so rows of one CTA run independently.
+//
+// Reference routines covered: fftPad::forward1/forward2[Many] + backward
+// (convolve.cc:849-1225,1482-1763), fftPadReal::forward1Many/backward1Many
+// (convolve.cc:5852-5964,6702-6788), the residue loop of
+// Convolution::convolveRaw with multBinary/multcorrelation fused
+// (convolve.cc:7513-7575,33-110).
+
 #include "gpu_internal.h"
+
+#include <mutex>
 
 namespace fftwpp_gpu {
 
 struct FastInfo {
-  int dummy;
+  int log2m;        // m = 2^log2m: the longer of the (at most two) FFT lengths
+  bool uniform;     // every sub-block has length m
+  int nterm;        // max number of input terms folded into one W[s]
 };
 
-void fast_plan_init(Plan *pl) {pl->fast=NULL;}
-void fast_plan_free(Plan *pl) {delete pl->fast; pl->fast=NULL;}
+namespace {
 
-int fast_try_forward(Plan *, uint64_t, uint64_t, int, const void *, void *,
-                     uint64_t, uint64_t, uint64_t, cudaStream_t)
+__device__ __forceinline__ double2 fmul(double2 a, double2 b)
 {
+  return make_double2(fma(a.x,b.x,-a.y*b.y),fma(a.x,b.y,a.y*b.x));
+}
+
+__device__ __forceinline__ double2 fmulc(double2 a, double2 b) // a*conj(b)
+{
+  return make_double2(fma(a.x,b.x,a.y*b.y),fma(a.y,b.x,-a.x*b.y));
+}
+
+__device__ __forceinline__ double2 operator+(double2 a, double2 b)
+{
+  return make_double2(a.x+b.x,a.y+b.y);
+}
+
+__device__ __forceinline__ double2 operator-(double2 a, double2 b)
+{
+  return make_double2(a.x-b.x,a.y-b.y);
+}
+
+// multiply by SIGN*i
+template<int SIGN>
+__device__ __forceinline__ double2 rot(double2 a)
+{
+  return SIGN > 0 ? make_double2(-a.y,a.x) : make_double2(a.y,-a.x);
+}
+
+// y_v = sum_u a_u exp(SIGN 2 pi i u v/8), in place, natural order.
+template<int SIGN>
+__device__ __forceinline__ void bfly8(double2 (&a)[8])
+{
+  const double h=0.70710678118654752440;
+  double2 b0=a[0]+a[4], b4=a[0]-a[4];
+  double2 b1=a[1]+a[5], b5=a[1]-a[5];
+  double2 b2=a[2]+a[6], b6=a[2]-a[6];
+  double2 b3=a[3]+a[7], b7=a[3]-a[7];
+  // even outputs: radix 4 on b0..b3
+  double2 c0=b0+b2, c2=b0-b2;
+  double2 c1=b1+b3, c3=rot<SIGN>(b1-b3);
+  a[0]=c0+c1;
+  a[4]=c0-c1;
+  a[2]=c2+c3;
+  a[6]=c2-c3;
+  // odd outputs: radix 4 on b4, w b5, w^2 b6, w^3 b7 with w=exp(SIGN i pi/4);
+  // the 1/sqrt(2) factors are folded into the final FMAs
+  double2 r6=rot<SIGN>(b6);
+  double2 d0=b4+r6, d2=b4-r6;
+  double2 p5=b5+rot<SIGN>(b5);           // sqrt(2) w b5
+  double2 p7=rot<SIGN>(b7)-b7;           // sqrt(2) w^3 b7
+  double2 s1=p5+p7;
+  double2 s3=rot<SIGN>(p5-p7);
+  a[1]=make_double2(fma(h,s1.x,d0.x),fma(h,s1.y,d0.y));
+  a[5]=make_double2(fma(-h,s1.x,d0.x),fma(-h,s1.y,d0.y));
+  a[3]=make_double2(fma(h,s3.x,d2.x),fma(h,s3.y,d2.y));
+  a[7]=make_double2(fma(-h,s3.x,d2.x),fma(-h,s3.y,d2.y));
+}
+
+template<int SIGN>
+__device__ __forceinline__ void bfly4(double2& a0, double2& a1, double2& a2,
+                                      double2& a3)
+{
+  double2 c0=a0+a2, c2=a0-a2;
+  double2 c1=a1+a3, c3=rot<SIGN>(a1-a3);
+  a0=c0+c1;
+  a1=c2+c3;
+  a2=c0-c1;
+  a3=c2-c3;
+}
+
+__device__ __forceinline__ void bfly2(double2& a0, double2& a1)
+{
+  double2 t=a0-a1;
+  a0=a0+a1;
+  a1=t;
+}
+
+// Shared-memory addressing policies.
+struct LaneLayout { // element p of lane `lane` at p*T+lane; CTA-wide barrier
+  int T, lane;
+  __device__ __forceinline__ int addr(int p) const {return p*T+lane;}
+  __device__ __forceinline__ void sync() const {__syncthreads();}
+};
+
+struct RowLayout { // one padded buffer per row; barrier over the row's threads
+  int base;        // row offset inside the exchange buffer (in double2)
+  int barid;       // named barrier id (0: the row lives inside one warp)
+  int nthreads;
+  __device__ __forceinline__ int addr(int p) const {return base+p+(p >> 3);}
+  __device__ __forceinline__ void sync() const {
+    if(barid == 0) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" :: "r"(barid), "r"(nthreads) : "memory");
+  }
+};
+
+// Register FFT of length N=2^LG over N/8 threads, NA arrays at a time (the
+// arrays share twiddle loads and barriers).
+template<int LG>
+struct RegFFT {
+  static const int N=1 << LG;
+  static const int TPT=N/8;
+  static const int NR8=LG/3;
+  static const int REM=LG % 3;
+
+  // position of register t of thread tau in a pass whose legs are 2^ls apart
+  static __device__ __forceinline__ int pos(int tau, int t, int ls) {
+    return ((tau >> ls) << (ls+3))+(tau & ((1 << ls)-1))+(t << ls);
+  }
+
+  // Array a uses buffer buf+a*bufStride.  Barrier before the writes protects
+  // the previous readers of the buffer, barrier after publishes the writes.
+  template<int NA, class Lay>
+  static __device__ __forceinline__ void exchange(double2 (&x)[NA][8], int tau,
+                                                  int lsFrom, int lsTo,
+                                                  double2 *buf, int bufStride,
+                                                  const Lay& lay, bool active) {
+    lay.sync();
+    if(active) {
+#pragma unroll
+      for(int a=0; a < NA; ++a)
+#pragma unroll
+        for(int t=0; t < 8; ++t)
+          buf[a*bufStride+lay.addr(pos(tau,t,lsFrom))]=x[a][t];
+    }
+    lay.sync();
+    if(active) {
+#pragma unroll
+      for(int a=0; a < NA; ++a)
+#pragma unroll
+        for(int t=0; t < 8; ++t)
+          x[a][t]=buf[a*bufStride+lay.addr(pos(tau,t,lsTo))];
+    }
+  }
+
+  // in: x[a][t]=W_a[tau+TPT*t]; out: x[a][e]=FFT at scrambled position 8*tau+e
+  template<int NA, class Lay>
+  static __device__ __forceinline__ void forward(double2 (&x)[NA][8], int tau,
+                                                 const double2 *__restrict__ tw,
+                                                 double2 *buf, int bufStride,
+                                                 const Lay& lay, bool active) {
+#pragma unroll
+    for(int i=0; i < NR8; ++i) {
+      const int ls=LG-3*(i+1);
+#pragma unroll
+      for(int a=0; a < NA; ++a) bfly8<1>(x[a]);
+      if(ls > 0) {
+#pragma unroll
+        for(int u=1; u < 8; ++u) {
+          const double2 w=__ldg(tw+(7*i+u-1)*TPT+tau);
+#pragma unroll
+          for(int a=0; a < NA; ++a) x[a][u]=fmul(x[a][u],w);
+        }
+      }
+      const int lsNext=(i+1 < NR8) ? LG-3*(i+2) : 0;
+      if(i+1 < NR8 || REM > 0)
+        exchange<NA>(x,tau,ls,lsNext,buf,bufStride,lay,active);
+    }
+#pragma unroll
+    for(int a=0; a < NA; ++a) {
+      if(REM == 2) {
+        bfly4<1>(x[a][0],x[a][1],x[a][2],x[a][3]);
+        bfly4<1>(x[a][4],x[a][5],x[a][6],x[a][7]);
+      } else if(REM == 1) {
+        bfly2(x[a][0],x[a][1]);
+        bfly2(x[a][2],x[a][3]);
+        bfly2(x[a][4],x[a][5]);
+        bfly2(x[a][6],x[a][7]);
+      }
+    }
+  }
+
+  // exact adjoint of forward(): in scrambled positions, out x[t]=w[tau+TPT*t]
+  template<int NA, class Lay>
+  static __device__ __forceinline__ void adjoint(double2 (&x)[NA][8], int tau,
+                                                 const double2 *__restrict__ tw,
+                                                 double2 *buf, int bufStride,
+                                                 const Lay& lay, bool active) {
+#pragma unroll
+    for(int a=0; a < NA; ++a) {
+      if(REM == 2) {
+        bfly4<-1>(x[a][0],x[a][1],x[a][2],x[a][3]);
+        bfly4<-1>(x[a][4],x[a][5],x[a][6],x[a][7]);
+      } else if(REM == 1) {
+        bfly2(x[a][0],x[a][1]);
+        bfly2(x[a][2],x[a][3]);
+        bfly2(x[a][4],x[a][5]);
+        bfly2(x[a][6],x[a][7]);
+      }
+    }
+#pragma unroll
+    for(int i=NR8-1; i >= 0; --i) {
+      const int ls=LG-3*(i+1);
+      const int lsPrev=(i+1 < NR8) ? LG-3*(i+2) : 0;
+      if(i+1 < NR8 || REM > 0)
+        exchange<NA>(x,tau,lsPrev,ls,buf,bufStride,lay,active);
+      if(ls > 0) {
+#pragma unroll
+        for(int u=1; u < 8; ++u) {
+          const double2 w=__ldg(tw+(7*i+u-1)*TPT+tau);
+#pragma unroll
+          for(int a=0; a < NA; ++a) x[a][u]=fmulc(x[a][u],w);
+        }
+      }
+#pragma unroll
+      for(int a=0; a < NA; ++a) bfly8<-1>(x[a]);
+    }
+  }
+
+  // transformed index held at scrambled position p (mixed-radix digit reversal)
+  static __device__ __forceinline__ int rev(int p) {
+    int rem=p, l=0, shift=0, lg=LG;
+#pragma unroll
+    for(int i=0; i < NR8; ++i) {
+      lg -= 3;
+      l += (rem >> lg) << shift;
+      rem &= (1 << lg)-1;
+      shift += 3;
+    }
+    if(REM > 0) l += rem << shift;
+    return l;
+  }
+};
+
+__device__ __forceinline__ double2 zeta(const PlanDev& P, long long e)
+{
+  if(P.zshift < 0) return __ldg(P.z1+e);
+  long long hi=e >> P.zshift;
+  long long lo=e & ((1ll << P.zshift)-1);
+  return fmul(__ldg(P.z1+hi),__ldg(P.z2+lo));
+}
+
+// (k0*j) mod N without 64-bit division on the common paths
+__device__ __forceinline__ long long modN(const PlanDev& P, long long k0,
+                                          int j)
+{
+  if(P.nmask) return (long long) (((unsigned) k0*(unsigned) j) & P.nmask);
+  if(P.small32) {
+    unsigned N=(unsigned) P.N;
+    unsigned e=((unsigned) k0*(unsigned) (j < 0 ? -j : j)) % N;
+    if(j < 0 && e) e=N-e;
+    return (long long) e;
+  }
+  long long e=(k0*j) % P.N;
+  return e < 0 ? e+P.N : e;
+}
+
+template<int KIND>
+struct Word {typedef double2 type;};
+template<>
+struct Word<FFTWPP_KIND_REAL> {typedef double type;};
+
+__device__ __forceinline__ double2 toC(double2 v) {return v;}
+__device__ __forceinline__ double2 toC(double v) {return make_double2(v,0.0);}
+
+// ---------------------------------------------------------------------------
+// fused 1-D convolution over contiguous rows (COMPLEX kind, A=2, B=1)
+// ---------------------------------------------------------------------------
+
+template<int LG, int NTERM, int OCC>
+__global__ void __launch_bounds__((1 << LG)/8 > 256 ? (1 << LG)/8 : 256, (1 << LG)/8 > 256 ? 1 : OCC)
+fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
+               double2 *f0, const double2 *f1, int mult, double scale,
+               long long nrows, long long rs, int tabid)
+{
+  typedef RegFFT<LG> FFT;
+  const int M=FFT::N;
+  const int TPT=FFT::TPT;
+  const int NT=TPT > 256 ? TPT : 256;
+  const int ROWS=NT/TPT;
+  // OCC==2 keeps the accumulators in shared memory between sub-blocks so the
+  // kernel fits 128 registers without local-memory spills.
+  const bool PARK=(OCC == 2);
+  extern __shared__ __align__(16) double2 sm[];
+  const int rowInCta=threadIdx.x/TPT;
+  const int tau=threadIdx.x % TPT;
+  long long row=(long long) blockIdx.x*ROWS+rowInCta;
+  const bool live=row < nrows;
+  if(!live) row=nrows-1;
+  const int BUF=M+M/8;
+  double2 *buf=sm;                 // two exchange buffers per row
+  double2 *park=sm+2*ROWS*BUF;     // NTERM*M accumulators per row (PARK)
+  RowLayout lay;
+  lay.base=rowInCta*BUF;
+  lay.barid=TPT > 32 ? 1+rowInCta : 0;
+  lay.nthreads=TPT;
+  const int bufStride=ROWS*BUF;
+  const double2 *tw=P.tab[tabid].tw8;
+  const int L=P.jmax;
+  double2 *g0=f0+row*rs;
+  const double2 *g1=f1+row*rs;
+  double2 *mypark=park+(size_t) rowInCta*NTERM*M+tau;
+
+  double2 acc[NTERM][8];
+#pragma unroll
+  for(int k=0; k < NTERM; ++k)
+#pragma unroll
+    for(int t=0; t < 8; ++t)
+      acc[k][t]=make_double2(0.0,0.0);
+
+  for(int isb=0; isb < nsb; ++isb) {
+    const long long k0=sbs[isb].k0;
+    if(PARK && isb > 0) {
+#pragma unroll
+      for(int k=0; k < NTERM; ++k)
+#pragma unroll
+        for(int t=0; t < 8; ++t)
+          mypark[(k*8+t)*TPT]=acc[k][t];
+    }
+    double2 x[2][8];
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+      x[0][t]=make_double2(0.0,0.0);
+      x[1][t]=make_double2(0.0,0.0);
+#pragma unroll
+      for(int k=0; k < NTERM; ++k) {
+        int j=tau+TPT*t+k*M;
+        if(j < L) {
+          double2 a=g0[j];
+          double2 b=g1[j];
+          if(k0 != 0) {
+            double2 z=zeta(P,modN(P,k0,j));
+            a=fmul(a,z);
+            b=fmul(b,z);
+          }
+          x[0][t]=x[0][t]+a;
+          x[1][t]=x[1][t]+b;
+        }
+      }
+    }
+    FFT::template forward<2>(x,tau,tw,buf,bufStride,lay,true);
+    double2 y[1][8];
+    if(mult == FFTWPP_MULT_BINARY) {
+#pragma unroll
+      for(int t=0; t < 8; ++t) y[0][t]=fmul(x[0][t],x[1][t]);
+    } else {
+#pragma unroll
+      for(int t=0; t < 8; ++t) y[0][t]=fmulc(x[0][t],x[1][t]);
+    }
+    FFT::template adjoint<1>(y,tau,tw,buf,bufStride,lay,true);
+    if(PARK && isb > 0) {
+#pragma unroll
+      for(int k=0; k < NTERM; ++k)
+#pragma unroll
+        for(int t=0; t < 8; ++t)
+          acc[k][t]=mypark[(k*8+t)*TPT];
+    }
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+#pragma unroll
+      for(int k=0; k < NTERM; ++k) {
+        int j=tau+TPT*t+k*M;
+        if(j < L) {
+          double2 v=y[0][t];
+          if(k0 != 0) v=fmulc(v,zeta(P,modN(P,k0,j)));
+          acc[k][t]=acc[k][t]+v;
+        }
+      }
+    }
+  }
+  if(live) {
+#pragma unroll
+    for(int k=0; k < NTERM; ++k)
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        int j=tau+TPT*t+k*M;
+        if(j < L)
+          g0[j]=make_double2(acc[k][t].x*scale,acc[k][t].y*scale);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// strided ("Many") forward / backward passes over tiles of T columns
+// ---------------------------------------------------------------------------
+
+// logical sample j of lane `lane` from the staged tile (lane fastest)
+template<int KIND>
+__device__ __forceinline__ double2 tileInput(const void *in, int j, int jmin,
+                                             int T, int lane)
+{
+  if(KIND == FFTWPP_KIND_REAL)
+    return make_double2(((const double *) in)[j*T+lane],0.0);
+  const double2 *c=(const double2 *) in;
+  if(KIND == FFTWPP_KIND_HERMITIAN) {
+    if(j >= 0) return c[j*T+lane];
+    double2 v=c[(-j)*T+lane];
+    return make_double2(v.x,-v.y);
+  }
+  return c[(j-jmin)*T+lane];
+}
+
+template<int KIND, int LG>
+__device__ __forceinline__ void forwardSub(const PlanDev& P,
+                                           const SubBlockDev& sb,
+                                           const void *in, double2 *buf,
+                                           void *F,
+                                           long long Fbase, int T, int col0,
+                                           bool colsok)
+{
+  typedef RegFFT<LG> FFT;
+  const int mlen=FFT::N;
+  const int TPT=FFT::TPT;
+  const int lane=threadIdx.x % T;
+  const int tau=threadIdx.x/T;
+  const bool active=tau < TPT;
+  LaneLayout lay;
+  lay.T=T;
+  lay.lane=lane;
+  const FftTab& tab=P.tab[sb.tab];
+  const long long k0=sb.k0;
+  double2 x[1][8];
+#pragma unroll
+  for(int t=0; t < 8; ++t) x[0][t]=make_double2(0.0,0.0);
+  if(active) {
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+      int s=tau+TPT*t;
+      int d=(s-P.jmin) & (mlen-1);
+      double2 acc=make_double2(0.0,0.0);
+      for(int j=P.jmin+d; j < P.jmax; j += mlen) {
+        double2 v=tileInput<KIND>(in,j,P.jmin,T,lane);
+        if(k0 != 0) v=fmul(v,zeta(P,modN(P,k0,j)));
+        acc=acc+v;
+      }
+      x[0][t]=acc;
+    }
+  }
+  FFT::template forward<1>(x,active ? tau : 0,tab.tw8,buf,0,lay,active);
+  if(active && colsok) {
+#pragma unroll
+    for(int e=0; e < 8; ++e) {
+      int l=FFT::rev(8*tau+e);
+      if(l < (int) sb.nout) {
+        long long a=Fbase+P.S*l+col0+lane;
+        double2 v=x[0][e];
+        if(KIND == FFTWPP_KIND_HERMITIAN)
+          ((double *) F)[a]=v.x;
+        else {
+          if(sb.flags & FFTWPP_SB_CONJ_OUT) v.y=-v.y;
+          ((double2 *) F)[a]=v;
+        }
+      }
+    }
+  }
+}
+
+template<int KIND, int LG>
+__global__ void __launch_bounds__(512)
+fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
+                  int layout, const void *f, void *F, long long nrows,
+                  long long frs, long long Frs, int T, int ntc, size_t inbytes)
+{
+  typedef typename Word<KIND>::type word;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  word *in=(word *) smraw;
+  const int M=1 << LG;
+  double2 *buf=(double2 *) (smraw+inbytes);
+  const long long row=blockIdx.x/ntc;
+  const int col0=(blockIdx.x % ntc)*T;
+  const int lane=threadIdx.x % T;
+  const bool colsok=col0+lane < P.C;
+
+  // stage the input tile: T contiguous words per logical row
+  const word *g=(const word *) f+row*frs+col0;
+  const int total=P.Lin*T;
+  for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
+    int j=idx/T;
+    int c=idx-j*T;
+    in[idx]=(col0+c < P.C) ? g[P.S*j+c] : word();
+  }
+  __syncthreads();
+
+  for(int isb=0; isb < nsb; ++isb) {
+    const SubBlockDev sb=sbs[isb];
+    const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
+    if((int) sb.mlen == M)
+      forwardSub<KIND,LG>(P,sb,in,buf,F,Fbase,T,col0,colsok);
+    else
+      forwardSub<KIND,LG-1>(P,sb,in,buf,F,Fbase,T,col0,colsok);
+  }
+}
+
+template<int KIND, int LG>
+__device__ __forceinline__ void backwardSub(const PlanDev& P,
+                                            const SubBlockDev& sb, void *acc,
+                                            double2 *buf, const void *F,
+                                            long long Fbase, int T, int col0,
+                                            bool colsok)
+{
+  typedef RegFFT<LG> FFT;
+  const int mlen=FFT::N;
+  const int TPT=FFT::TPT;
+  const int lane=threadIdx.x % T;
+  const int tau=threadIdx.x/T;
+  const bool active=tau < TPT;
+  LaneLayout lay;
+  lay.T=T;
+  lay.lane=lane;
+  const FftTab& tab=P.tab[sb.tab];
+  const long long k0=sb.k0;
+  double2 x[1][8];
+#pragma unroll
+  for(int t=0; t < 8; ++t) x[0][t]=make_double2(0.0,0.0);
+  if(active) {
+#pragma unroll
+    for(int e=0; e < 8; ++e) {
+      int l=FFT::rev(8*tau+e);
+      double2 v=make_double2(0.0,0.0);
+      if(colsok) {
+        long long a=Fbase+col0+lane;
+        if(KIND == FFTWPP_KIND_HERMITIAN)
+          v.x=((const double *) F)[a+P.S*l];
+        else if(sb.flags & FFTWPP_SB_CONJ_OUT) {
+          if(l < (int) sb.nout) {
+            v=((const double2 *) F)[a+P.S*l];
+            v.y=-v.y;
+          } else
+            v=((const double2 *) F)[a+P.S*(mlen-l)];
+        } else
+          v=((const double2 *) F)[a+P.S*l];
+      }
+      x[0][e]=v;
+    }
+  }
+  FFT::template adjoint<1>(x,active ? tau : 0,tab.tw8,buf,0,lay,active);
+  if(active) {
+    const int lo=(KIND == FFTWPP_KIND_HERMITIAN) ? 0 : P.jmin;
+    const int shift=(KIND == FFTWPP_KIND_CENTERED) ? P.jmin : 0;
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+      int s=tau+TPT*t;
+      int d=(s-lo) & (mlen-1);
+      for(int j=lo+d; j < P.jmax; j += mlen) {
+        double2 v=x[0][t];
+        if(k0 != 0) v=fmulc(v,zeta(P,modN(P,k0,j)));
+        int idx=(j-shift)*T+lane;
+        if(KIND == FFTWPP_KIND_REAL) {
+          double *a=(double *) acc;
+          a[idx] += (sb.flags & FFTWPP_SB_CONJ_OUT) ? v.x : 2.0*v.x;
+        } else {
+          double2 *a=(double2 *) acc;
+          a[idx]=a[idx]+v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template<int KIND, int LG>
+__global__ void __launch_bounds__(512)
+fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
+                   int layout, const void *F, void *f, int accum, double scale,
+                   long long nrows, long long Frs, long long frs, int T,
+                   int ntc, size_t accbytes)
+{
+  typedef typename Word<KIND>::type word;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  word *acc=(word *) smraw;
+  const int M=1 << LG;
+  double2 *buf=(double2 *) (smraw+accbytes);
+  const long long row=blockIdx.x/ntc;
+  const int col0=(blockIdx.x % ntc)*T;
+  const int lane=threadIdx.x % T;
+  const bool colsok=col0+lane < P.C;
+  word *g=(word *) f+row*frs+col0;
+  const int total=P.Lin*T;
+  for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
+    int j=idx/T;
+    int c=idx-j*T;
+    acc[idx]=(accum && col0+c < P.C) ? g[P.S*j+c] : word();
+  }
+  __syncthreads();
+
+  for(int isb=0; isb < nsb; ++isb) {
+    const SubBlockDev sb=sbs[isb];
+    const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
+    if((int) sb.mlen == M)
+      backwardSub<KIND,LG>(P,sb,acc,buf,F,Fbase,T,col0,colsok);
+    else
+      backwardSub<KIND,LG-1>(P,sb,acc,buf,F,Fbase,T,col0,colsok);
+  }
+  for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
+    int j=idx/T;
+    int c=idx-j*T;
+    if(col0+c < P.C)
+      g[P.S*j+c]=wscale(acc[idx],scale);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------
+
+const size_t SMEM_MAX=227*1024;
+
+template<class K>
+int allowSmem(K kernel)
+{
+  static std::mutex mu;
+  static std::vector<const void *> done[16];
+  int dev=0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  std::vector<const void *>& v=done[dev & 15];
+  for(size_t i=0; i < v.size(); ++i)
+    if(v[i] == (const void *) kernel) return 0;
+  cudaError_t e=cudaFuncSetAttribute(kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int) SMEM_MAX);
+  if(e != cudaSuccess) return cuda_fail(e,"cudaFuncSetAttribute");
+  v.push_back((const void *) kernel);
   return 0;
 }
 
-int fast_try_backward(Plan *, uint64_t, uint64_t, int, const void *, void *,
-                      int, double, uint64_t, uint64_t, uint64_t, cudaStream_t)
+int ilog2(unsigned v)
 {
+  int l=0;
+  while((1u << l) < v) ++l;
+  return l;
+}
+
+bool ispow2(unsigned v) {return v && !(v & (v-1));}
+
+size_t wordBytes(int kind)
+{
+  return kind == FFTWPP_KIND_REAL ? sizeof(double) : sizeof(double2);
+}
+
+int tileLanes()
+{
+  static int T=-1;
+  if(T < 0) {
+    const char *s=getenv("FFTWPP_TILE_LANES");
+    T=s ? atoi(s) : 4;
+    if(T != 2 && T != 4 && T != 8 && T != 16) T=8;
+  }
+  return T;
+}
+
+bool fastDisabled()
+{
+  static int off=-1;
+  if(off < 0) {
+    const char *s=getenv("FFTWPP_NO_FAST");
+    off=(s && *s && *s != '0') ? 1 : 0;
+  }
+  return off == 1;
+}
+
+#define LG_CASES(CALL)            \
+  switch(lg) {                    \
+    case 4: {CALL(4); break;}     \
+    case 5: {CALL(5); break;}     \
+    case 6: {CALL(6); break;}     \
+    case 7: {CALL(7); break;}     \
+    case 8: {CALL(8); break;}     \
+    case 9: {CALL(9); break;}     \
+    case 10: {CALL(10); break;}   \
+    case 11: {CALL(11); break;}   \
+    case 12: {CALL(12); break;}   \
+    default: return 0;            \
+  }
+
+template<int KIND>
+int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
+                      const void *f, void *F, uint64_t nrows, uint64_t frs,
+                      uint64_t Frs, cudaStream_t st)
+{
+  int T=tileLanes();
+  while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
+  const int M=1 << lg;
+  size_t inbytes,smem;
+  for(;;) {
+    inbytes=((size_t) pl->dev.Lin*T*wordBytes(KIND)+15) & ~(size_t) 15;
+    smem=inbytes+(size_t) M*T*sizeof(double2);
+    if(smem <= SMEM_MAX && T*(M/8) <= 512) break;
+    if(T == 1) return 0;
+    T /= 2;
+  }
+  int nthreads=T*(M/8);
+  if(nthreads < 32) return 0;
+  int ntc=(int) ((pl->dev.C+T-1)/T);
+  uint64_t grid=nrows*ntc;
+  if(grid == 0) return 1;
+  if(grid > 0x7fffffffull) return 0;
+  int rc=0;
+#define CALL(LGV)                                                            \
+  rc=allowSmem(fast_forward_many<KIND,LGV>);                                 \
+  if(rc) return rc;                                                          \
+  prof_begin(4*pl->tag+0,st);                                                \
+  fast_forward_many<KIND,LGV><<<(unsigned) grid,nthreads,smem,st>>>          \
+    (pl->dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,            \
+     (long long) frs,(long long) Frs,T,ntc,inbytes);
+  LG_CASES(CALL)
+#undef CALL
+  rc=check_launch("fast_forward_many",st);
+  return rc ? rc : 1;
+}
+
+template<int KIND>
+int launchBackwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb,
+                       int layout, const void *F, void *f, int accumulate,
+                       double scale, uint64_t nrows, uint64_t Frs,
+                       uint64_t frs, cudaStream_t st)
+{
+  int T=tileLanes();
+  while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
+  const int M=1 << lg;
+  size_t accbytes,smem;
+  for(;;) {
+    accbytes=((size_t) pl->dev.Lin*T*wordBytes(KIND)+15) & ~(size_t) 15;
+    smem=accbytes+(size_t) M*T*sizeof(double2);
+    if(smem <= SMEM_MAX && T*(M/8) <= 512) break;
+    if(T == 1) return 0;
+    T /= 2;
+  }
+  int nthreads=T*(M/8);
+  if(nthreads < 32) return 0;
+  int ntc=(int) ((pl->dev.C+T-1)/T);
+  uint64_t grid=nrows*ntc;
+  if(grid == 0) return 1;
+  if(grid > 0x7fffffffull) return 0;
+  int rc=0;
+#define CALL(LGV)                                                            \
+  rc=allowSmem(fast_backward_many<KIND,LGV>);                                \
+  if(rc) return rc;                                                          \
+  prof_begin(4*pl->tag+1,st);                                                \
+  fast_backward_many<KIND,LGV><<<(unsigned) grid,nthreads,smem,st>>>         \
+    (pl->dev,pl->dsub+sb0,(int) nsb,layout,F,f,accumulate,scale,             \
+     (long long) nrows,(long long) Frs,(long long) frs,T,ntc,accbytes);
+  LG_CASES(CALL)
+#undef CALL
+  rc=check_launch("fast_backward_many",st);
+  return rc ? rc : 1;
+}
+
+int convOcc()
+{
+  static int occ=-1;
+  if(occ < 0) {
+    const char *s=getenv("FFTWPP_CONV_OCC");
+    occ=(s && atoi(s) == 1) ? 1 : 2;
+  }
+  return occ;
+}
+
+template<int NTERM, int OCC>
+int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
+                   uint64_t nrows, uint64_t rs, cudaStream_t st)
+{
+  const int M=1 << lg;
+  const int TPT=M/8;
+  const int NT=TPT > 256 ? TPT : 256;
+  const int ROWS=NT/TPT;
+  size_t smem=2*(size_t) ROWS*(M+M/8)*sizeof(double2);
+  if(OCC == 2) smem += (size_t) ROWS*NTERM*M*sizeof(double2);
+  if(smem > SMEM_MAX) return 0;
+  uint64_t grid=(nrows+ROWS-1)/ROWS;
+  if(grid == 0) return 1;
+  if(grid > 0x7fffffffull) return 0;
+  int tabid=0;
+  int rc=0;
+#define CALL(LGV)                                                            \
+  rc=allowSmem(fast_conv_rows<LGV,NTERM,OCC>);                               \
+  if(rc) return rc;                                                          \
+  prof_begin(4*pl->tag+2,st);                                                \
+  fast_conv_rows<LGV,NTERM,OCC><<<(unsigned) grid,NT,smem,st>>>              \
+    (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],                \
+     (const double2 *) f[1],mult,scale,(long long) nrows,(long long) rs,     \
+     tabid);
+  LG_CASES(CALL)
+#undef CALL
+  rc=check_launch("fast_conv_rows",st);
+  return rc ? rc : 1;
+}
+
+} // namespace
+
+void fast_plan_init(Plan *pl)
+{
+  pl->fast=NULL;
+  if(fastDisabled()) return;
+  unsigned mmax=pl->mmax;
+  if(!ispow2(mmax) || mmax < 16 || mmax > 4096) return;
+  bool uniform=true;
+  unsigned mmin=mmax;
+  for(size_t i=0; i < pl->hsub.size(); ++i) {
+    unsigned ml=pl->hsub[i].mlen;
+    if(ml != mmax) {
+      uniform=false;
+      if(2*ml != mmax) return;
+      mmin=ml;
+    }
+  }
+  if(pl->dev.Lin > 32768) return;
+  FastInfo *fi=new FastInfo;
+  fi->log2m=ilog2(mmax);
+  fi->uniform=uniform;
+  int span=pl->dev.jmax-pl->dev.jmin;
+  fi->nterm=(span+(int) mmin-1)/(int) mmin;
+  pl->fast=fi;
+}
+
+void fast_plan_free(Plan *pl)
+{
+  delete pl->fast;
+  pl->fast=NULL;
+}
+
+int fast_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                     const void *f, void *F, uint64_t nrows, uint64_t frs,
+                     uint64_t Frs, cudaStream_t st)
+{
+  FastInfo *fi=pl->fast;
+  if(!fi || pl->dev.C < 2) return 0;
+  int lg=fi->log2m;
+  switch(pl->dev.kind) {
+    case FFTWPP_KIND_COMPLEX:
+      return launchForwardMany<FFTWPP_KIND_COMPLEX>(pl,lg,sb0,nsb,layout,f,F,
+                                                    nrows,frs,Frs,st);
+    case FFTWPP_KIND_CENTERED:
+      return launchForwardMany<FFTWPP_KIND_CENTERED>(pl,lg,sb0,nsb,layout,f,F,
+                                                     nrows,frs,Frs,st);
+    case FFTWPP_KIND_REAL:
+      return launchForwardMany<FFTWPP_KIND_REAL>(pl,lg,sb0,nsb,layout,f,F,
+                                                 nrows,frs,Frs,st);
+  }
   return 0;
 }
 
-int fast_try_convolve(Plan *, void *const *, uint32_t, uint32_t, int, double,
-                      uint64_t, uint64_t, cudaStream_t)
+int fast_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                      const void *F, void *f, int accumulate, double scale,
+                      uint64_t nrows, uint64_t Frs, uint64_t frs,
+                      cudaStream_t st)
 {
+  FastInfo *fi=pl->fast;
+  if(!fi || pl->dev.C < 2) return 0;
+  int lg=fi->log2m;
+  switch(pl->dev.kind) {
+    case FFTWPP_KIND_COMPLEX:
+      return launchBackwardMany<FFTWPP_KIND_COMPLEX>(pl,lg,sb0,nsb,layout,F,f,
+                                                     accumulate,scale,nrows,
+                                                     Frs,frs,st);
+    case FFTWPP_KIND_CENTERED:
+      return launchBackwardMany<FFTWPP_KIND_CENTERED>(pl,lg,sb0,nsb,layout,F,f,
+                                                      accumulate,scale,nrows,
+                                                      Frs,frs,st);
+    case FFTWPP_KIND_REAL:
+      return launchBackwardMany<FFTWPP_KIND_REAL>(pl,lg,sb0,nsb,layout,F,f,
+                                                  accumulate,scale,nrows,Frs,
+                                                  frs,st);
+  }
   return 0;
 }
 
+int fast_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
+                      int mult, double scale, uint64_t nrows, uint64_t rs,
+                      cudaStream_t st)
+{
+  FastInfo *fi=pl->fast;
+  if(!fi || !fi->uniform) return 0;
+  if(pl->dev.kind != FFTWPP_KIND_COMPLEX || pl->dev.C != 1 || pl->dev.S != 1)
+    return 0;
+  if(A != 2 || B != 1) return 0;
+  if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
+  if(fi->nterm == 1)
+    return convOcc() == 1 ?
+      launchConvRows<1,1>(pl,fi->log2m,f,mult,scale,nrows,rs,st) :
+      launchConvRows<1,2>(pl,fi->log2m,f,mult,scale,nrows,rs,st);
+  if(fi->nterm == 2)
+    return convOcc() == 1 ?
+      launchConvRows<2,1>(pl,fi->log2m,f,mult,scale,nrows,rs,st) :
+      launchConvRows<2,2>(pl,fi->log2m,f,mult,scale,nrows,rs,st);
+  return 0;
 }
+
+} // namespace fftwpp_gpu

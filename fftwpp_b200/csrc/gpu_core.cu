@@ -628,6 +628,45 @@ static int upload_roots(size_t count, size_t period, const double2 **out,
   return FFTWPP_GPU_OK;
 }
 
+// Twiddles of the register radix-8 passes laid out per thread (see FftTab).
+static int upload_tw8(unsigned n, const double2 **out,
+                      std::vector<void *>& owned)
+{
+  *out=NULL;
+  if(n < 16 || (n & (n-1))) return FFTWPP_GPU_OK;
+  int lg=0;
+  while((1u << lg) < n) ++lg;
+  int nr8=lg/3;
+  unsigned tpt=n/8;
+  std::vector<double2> h((size_t) 7*nr8*tpt);
+  const long double twopi=6.283185307179586476925286766559005768L;
+  for(int i=0; i < nr8; ++i) {
+    int ls=lg-3*(i+1);
+    for(int u=1; u < 8; ++u)
+      for(unsigned tau=0; tau < tpt; ++tau) {
+        unsigned long long j=tau & ((1u << ls)-1);
+        unsigned long long ph=((j*u) << (3*i)) % n;
+        long double a=twopi*(long double) ph/(long double) n;
+        double2 v;
+        v.x=(double) cosl(a);
+        v.y=(double) sinl(a);
+        if(4*ph == n) {v.x=0.0; v.y=1.0;}
+        else if(2*ph == n) {v.x=-1.0; v.y=0.0;}
+        else if(4*ph == 3ull*n) {v.x=0.0; v.y=-1.0;}
+        else if(ph == 0) {v.x=1.0; v.y=0.0;}
+        h[((size_t) 7*i+u-1)*tpt+tau]=v;
+      }
+  }
+  void *d=NULL;
+  cudaError_t e=cudaMalloc(&d,h.size()*sizeof(double2));
+  if(e != cudaSuccess) return cuda_fail(e,"cudaMalloc(tw8)");
+  e=cudaMemcpy(d,h.data(),h.size()*sizeof(double2),cudaMemcpyHostToDevice);
+  if(e != cudaSuccess) {cudaFree(d); return cuda_fail(e,"cudaMemcpy(tw8)");}
+  owned.push_back(d);
+  *out=(const double2 *) d;
+  return FFTWPP_GPU_OK;
+}
+
 Plan::~Plan()
 {
   for(size_t i=0; i < owned.size(); ++i)
@@ -672,6 +711,12 @@ int plan_build(const fftwpp_gpu_pad_desc *d, Plan **out)
       P.jmin=-((int) d->Lin-1); P.jmax=(int) d->Lin; break;
   }
 
+  P.nmask=(d->N < (1ull << 31) && (d->N & (d->N-1)) == 0) ?
+    (unsigned) (d->N-1) : 0u;
+  {
+    unsigned long long jabs=std::max<long long>(-(long long) P.jmin,P.jmax);
+    P.small32=(d->N*jabs < (1ull << 32)) ? 1 : 0;
+  }
   int rc;
   // zeta_N table: single level when small, else two-level with B=2^zshift
   if(d->N <= (1u << 16)) {
@@ -719,6 +764,8 @@ int plan_build(const fftwpp_gpu_pad_desc *d, Plan **out)
         return FFTWPP_GPU_EUNSUPPORTED;
       }
       rc=upload_roots(s.mlen,s.mlen,&P.tab[it].omega,pl->owned);
+      if(rc) {delete pl; return rc;}
+      rc=upload_tw8(s.mlen,&P.tab[it].tw8,pl->owned);
       if(rc) {delete pl; return rc;}
     }
     hs[i].mlen=s.mlen;

@@ -22,6 +22,10 @@ static const int MAXARRAYS=8;  // max(A,B) of a fused convolution
 // Roots of unity and radix schedule of one FFT length.
 struct FftTab {
   const double2 *omega; // omega[k]=exp(2 pi i k/n)
+  // power-of-two lengths: per-thread twiddles of the register radix-8 passes,
+  // tw8[(7*i+u-1)*(n/8)+tau]=omega^{((tau mod 2^ls_i)*u) 8^i}: threads of a
+  // warp read consecutive entries (fast_kernels.cu)
+  const double2 *tw8;
   int n;
   int nrad;
   int rad[MAXRAD];
@@ -44,6 +48,8 @@ struct PlanDev {
   int jmin, jmax;   // logical index range of the input
   int C;
   int zshift;       // <0: z1[e]; else z1[e>>zshift]*z2[e&mask]
+  unsigned nmask;   // N-1 when N is a power of two (and < 2^31), else 0
+  int small32;      // k0*|j| < 2^32 for every sub-block and input index
   long long N;
   long long S;
   const double2 *z1;
