@@ -82,3 +82,15 @@ _sig("fftwpp_gpu_profile_enable", c_int, c_int)
 _sig("fftwpp_gpu_profile_read", c_int, P(c_double), P(c_u64))
 _sig("fftwpp_gpu_malloc_host", c_int, P(c_void_p), c_size_t)
 _sig("fftwpp_gpu_free_host", c_int, c_void_p)
+_sig("fftwpp_gpu_comm_unique_id", c_int, ctypes.c_char_p)
+_sig("fftwpp_gpu_comm_create", c_int, c_int, c_int, ctypes.c_char_p, P(c_void_p))
+_sig("fftwpp_gpu_comm_destroy", c_int, c_void_p)
+_sig("fftwpp_mpiconv3_create", c_void_p, c_int, P(c_size_t), P(c_size_t), P(c_size_t),
+     P(c_size_t), P(c_long), c_size_t, c_size_t, c_int, c_int, c_int, c_void_p)
+_sig("fftwpp_mpiconv3_destroy", None, c_void_p)
+_sig("fftwpp_mpiconv3_split", None, c_void_p, P(c_size_t))
+_sig("fftwpp_mpiconv3_params", None, c_void_p, c_int, P(c_size_t))
+_sig("fftwpp_mpiconv3_convolve", None, c_void_p, P(c_void_p), c_int)
+_sig("fftwpp_mpiconv3_exchange_table", None, c_void_p, c_int, P(ctypes.c_ulonglong),
+     P(ctypes.c_ulonglong), P(ctypes.c_ulonglong), P(ctypes.c_ulonglong))
+_sig("fftwpp_mpiconv3_set_plane_chunk", None, c_void_p, c_size_t)

@@ -3,6 +3,7 @@
 // :27-163 and the owning bundles of wrappers/HybridConvolution.h:12-184
 // (default M = A*L-A+1 for complex, 3*ceil(L/2)-2*(L%2) for Hermitian).
 #include "convolve.h"
+#include "mpiconvolve.h"
 #include "../../include/cfftwpp.h"
 #include "../../include/fftwpp_gpu.h"
 
@@ -356,6 +357,99 @@ void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk)
 {
   Conv *c=(Conv *) conv;
   if(c->c3) c->c3->convolveyz[0]->planeChunk=chunk;
+}
+
+namespace {
+struct MpiConv {
+  Application *app[3];
+  fftBase *fft[3];
+  Convolution3MPI *conv;
+  ~MpiConv() {
+    delete conv;
+    for(int d=2; d >= 0; --d) {delete fft[d]; delete app[d];}
+  }
+};
+}
+
+void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
+                             const size_t *m, const size_t *D, const long *I,
+                             size_t A, size_t B, int mult, int rank, int size,
+                             void *comm)
+{
+  if(family != 0 && family != 2) {
+    std::cerr << "distributed convolutions: family must be 0 (complex) or 2 "
+              << "(real)" << std::endl;
+    exit(-1);
+  }
+  size_t zero[3]={0,0,0};
+  long minus[3]={-1,-1,-1};
+  if(!m) m=zero;
+  if(!D) D=zero;
+  if(!I) I=minus;
+  MpiConv *c=new MpiConv;
+  utils::MPIgroup group(rank,size,comm);
+  size_t y0;
+  size_t y=utils::localdimension(L[1],rank,size,&y0);
+  for(int d=0; d < 3; ++d) {
+    multiplier *mu=(d == 2) ? pickMult(mult) : multNone;
+    long Id=m[d] > 0 ? I[d] : -1;
+    if(d == 0)
+      c->app[d]=new Application(A,B,mu,fftw::maxthreads,false,m[d],D[d],Id);
+    else
+      c->app[d]=new Application(A,B,mu,*c->app[d-1],m[d],D[d],Id);
+  }
+  size_t Cx=std::max<size_t>(y,1)*L[2];
+  c->fft[0]=makePad(family == 2 ? 3 : 0,L[0],M[0],*c->app[0],Cx,Cx,m[0],D[0],
+                    I[0]);
+  c->fft[1]=makePad(0,L[1],M[1],*c->app[1],L[2],L[2],m[1],D[1],I[1]);
+  c->fft[2]=makePad(0,L[2],M[2],*c->app[2],1,0,m[2],D[2],I[2]);
+  if(y == 0) {
+    std::cerr << "rank " << rank << " has an empty y slab (more ranks than "
+              << "ceil-split rows); reduce the number of ranks" << std::endl;
+    exit(-1);
+  }
+  c->conv=new Convolution3MPI(c->fft[0],c->fft[1],c->fft[2],group);
+  return c;
+}
+
+void fftwpp_mpiconv3_destroy(void *conv) {delete (MpiConv *) conv;}
+
+void fftwpp_mpiconv3_split(void *conv, size_t *out)
+{
+  utils::split3& d=((MpiConv *) conv)->conv->d;
+  out[0]=d.X; out[1]=d.Y; out[2]=d.Z; out[3]=d.x; out[4]=d.y; out[5]=d.z;
+  out[6]=d.x0; out[7]=d.y0; out[8]=d.z0;
+}
+
+void fftwpp_mpiconv3_params(void *conv, int d, size_t *out)
+{
+  fftBase *f=((MpiConv *) conv)->fft[d];
+  out[0]=f->m; out[1]=f->p; out[2]=f->q; out[3]=f->n; out[4]=f->D;
+  out[5]=f->inplace; out[6]=f->C; out[7]=f->S;
+}
+
+void fftwpp_mpiconv3_convolve(void *conv, double **f, int normalized)
+{
+  Convolution3MPI *c=((MpiConv *) conv)->conv;
+  if(normalized) c->convolve((Complex **) f);
+  else c->convolveRaw((Complex **) f);
+}
+
+void fftwpp_mpiconv3_exchange_table(void *conv, int direction,
+                                    unsigned long long *scount,
+                                    unsigned long long *sdispl,
+                                    unsigned long long *rcount,
+                                    unsigned long long *rdispl)
+{
+  ((MpiConv *) conv)->conv->exchangeTable(direction,(uint64_t *) scount,
+                                          (uint64_t *) sdispl,
+                                          (uint64_t *) rcount,
+                                          (uint64_t *) rdispl);
+}
+
+void fftwpp_mpiconv3_set_plane_chunk(void *conv, size_t chunk)
+{
+  ((MpiConv *) conv)->conv->convolveyz[0]->planeChunk=chunk;
 }
 
 void fftwpp_set_stream(void *stream) {gpu::setStream(stream);}

@@ -1229,7 +1229,8 @@ Convolution3::Convolution3(fftBase *fftx, fftBase *ffty, fftBase *fftz,
   Sy=ffty->S;
   scale=1.0;
   if(!mpi) {
-    scale=1.0/normalization();
+    scale=1.0/(fftx->normalization()*ffty->normalization()*
+               fftz->normalization());
     checkStrides();
     // keep the y/z intermediates of a batch of x rows inside the L2
     size_t def=envSize("FFTWPP_PLANE_CHUNK",0);
@@ -1240,7 +1241,7 @@ Convolution3::Convolution3(fftBase *fftx, fftBase *ffty, fftBase *fftz,
 
 Convolution3::~Convolution3()
 {
-  delete convolveyz[0];
+  if(convolveyz[0]) delete convolveyz[0];
   delete [] convolveyz;
 }
 

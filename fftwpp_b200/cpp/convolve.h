@@ -523,11 +523,12 @@ public:
   virtual size_t inputLengthy() {return ffty->inputLength();}
   virtual size_t inputLengthz() {return fftz->inputLength();}
 
-  void convolveRaw(Complex **f, size_t offset=0, Indices *indices=NULL);
+  virtual void convolveRaw(Complex **f, size_t offset=0,
+                           Indices *indices=NULL);
   void convolveRaw(double **f, size_t offset=0, Indices *indices=NULL) {
     convolveRaw((Complex **) f,offset,indices);
   }
-  void convolve(Complex **f, size_t offset=0);
+  virtual void convolve(Complex **f, size_t offset=0);
   void convolve(double **f, size_t offset=0) {convolve((Complex **) f,offset);}
   void normalize(Complex **h, size_t offset=0);
 

@@ -1,0 +1,106 @@
+"""Distributed (slab over y) 3-D hybrid convolution: Python handle on the C++
+Convolution3MPI counterpart (cpp/mpiconvolve.h; reference mpi/mpiconvolve.h
+:182-305, driver mpi/tests/hybridconvr3.cc).  One process per GPU;
+torch.distributed is used only to bootstrap the NCCL communicator (broadcast of
+the unique id) -- the exchange itself is issued by lib_fftwpp.so."""
+import ctypes
+
+from ._lib import lib
+from .api import _ptr, FAMILY_REAL, MULT_BINARY
+
+
+def local_dimension(N, rank, size):
+    """extent, start of rank's share (reference mpi/mpitranspose.h:118-130)."""
+    n = (N + size - 1) // size
+    s = n * rank
+    if s >= N:
+        return 0, N
+    return (n if s + n <= N else N - s), s
+
+
+class SlabConvolution3:
+    def __init__(self, Lx, Ly, Lz, Mx, My, Mz, rank, world, family=FAMILY_REAL,
+                 m=None, D=None, I=None, A=2, B=1, mult=MULT_BINARY, comm="nccl"):
+        self.L, self.M = [Lx, Ly, Lz], [Mx, My, Mz]
+        self.rank, self.world, self.family, self.A, self.B = rank, world, family, A, B
+        self._comm = ctypes.c_void_p()
+        if comm == "nccl":
+            import torch
+            import torch.distributed as dist
+            buf = ctypes.create_string_buffer(128)
+            if rank == 0:
+                rc = lib.fftwpp_gpu_comm_unique_id(buf)
+                if rc:
+                    raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+            t = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            raw = bytes(t.cpu().tolist())
+            rc = lib.fftwpp_gpu_comm_create(rank, world, raw, ctypes.byref(self._comm))
+            if rc:
+                raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+        arr, larr = ctypes.c_size_t * 3, ctypes.c_long * 3
+        m = arr(*([0] * 3 if m is None else m))
+        D = arr(*([0] * 3 if D is None else D))
+        I = larr(*([-1] * 3 if I is None else I))
+        self._h = lib.fftwpp_mpiconv3_create(family, arr(*self.L), arr(*self.M), m, D, I,
+                                             A, B, mult, rank, world, self._comm)
+        buf = (ctypes.c_size_t * 9)()
+        lib.fftwpp_mpiconv3_split(self._h, buf)
+        self.split = dict(zip("X Y Z x y z x0 y0 z0".split(), [int(v) for v in buf]))
+
+    def params(self):
+        out = []
+        for d in range(3):
+            buf = (ctypes.c_size_t * 8)()
+            lib.fftwpp_mpiconv3_params(self._h, d, buf)
+            out.append(dict(zip("m p q n D inplace C S".split(), [int(v) for v in buf])))
+        return out
+
+    def exchange_table(self, direction):
+        n = self.world
+        t = [(ctypes.c_ulonglong * n)() for _ in range(4)]
+        lib.fftwpp_mpiconv3_exchange_table(self._h, direction, *t)
+        return [[int(v) for v in a] for a in t]
+
+    def local_shape(self):
+        return (self.L[0], self.split["y"], self.L[2])
+
+    def make_inputs(self, seed=1234, scale_second=None):
+        """Seeded inputs: the local slab of a globally defined random field."""
+        import numpy as np
+        import torch
+        Lx, Ly, Lz = self.L
+        y, y0 = self.split["y"], self.split["y0"]
+        out = []
+        for a in range(self.A):
+            g = torch.Generator(device="cpu").manual_seed(seed + a)
+            full = torch.rand((Lx, Ly, Lz), dtype=torch.float64, generator=g) * 2 - 1
+            if a == 1:
+                full = full * (scale_second if scale_second is not None
+                               else 1.7 / np.sqrt(float(Lx * Ly * Lz)))
+            if self.family == 0:
+                g2 = torch.Generator(device="cpu").manual_seed(seed + 100 + a)
+                im = torch.rand((Lx, Ly, Lz), dtype=torch.float64, generator=g2) * 2 - 1
+                full = torch.complex(full, im * (full.abs().max()))
+            out.append(full[:, y0:y0 + y, :].contiguous().cuda())
+        return out
+
+    def convolve(self, arrays, normalized=True):
+        n = max(self.A, self.B)
+        ptrs = (ctypes.c_void_p * n)(*[_ptr(a) for a in arrays[:n]])
+        lib.fftwpp_mpiconv3_convolve(self._h, ptrs, 1 if normalized else 0)
+        return arrays[0]
+
+    def convolve_raw(self, arrays):
+        return self.convolve(arrays, normalized=False)
+
+    def set_plane_chunk(self, chunk):
+        lib.fftwpp_mpiconv3_set_plane_chunk(self._h, int(chunk))
+
+    def close(self):
+        if self._h:
+            lib.fftwpp_mpiconv3_destroy(self._h)
+            self._h = None
+        if self._comm:
+            lib.fftwpp_gpu_comm_destroy(self._comm)
+            self._comm = ctypes.c_void_p()

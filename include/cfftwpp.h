@@ -129,6 +129,29 @@ void fftwpp_conv_convolve(void *conv, double **f, int normalized);
 /* batch size (x rows) of the y/z sweep of a 3-D convolution; 0 = all rows */
 void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk);
 
+/* ---- distributed (slab over y) 3-D convolution over NCCL: the counterpart
+ * of the reference's Convolution3MPI (mpi/mpiconvolve.h:182-305) built as in
+ * mpi/tests/hybridconv{,r}3.cc.  comm: handle from fftwpp_gpu_comm_create.
+ * family 0 (complex) or 2 (real).  Arrays are the LOCAL slabs
+ * Lx x y x Lz (device pointers). ---- */
+void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
+                             const size_t *m, const size_t *D, const long *I,
+                             size_t A, size_t B, int mult, int rank, int size,
+                             void *comm);
+void fftwpp_mpiconv3_destroy(void *conv);
+/* out = {X,Y,Z,x,y,z,x0,y0,z0} (split3) */
+void fftwpp_mpiconv3_split(void *conv, size_t *out);
+void fftwpp_mpiconv3_params(void *conv, int d, size_t *out);
+void fftwpp_mpiconv3_convolve(void *conv, double **f, int normalized);
+/* byte counts/displacements of exchange `direction` (0 forward, 1 backward);
+ * arrays of `size` entries */
+void fftwpp_mpiconv3_exchange_table(void *conv, int direction,
+                                    unsigned long long *scount,
+                                    unsigned long long *sdispl,
+                                    unsigned long long *rcount,
+                                    unsigned long long *rdispl);
+void fftwpp_mpiconv3_set_plane_chunk(void *conv, size_t chunk);
+
 /* stream used by every launch issued through this API (a cudaStream_t) */
 void fftwpp_set_stream(void *stream);
 

@@ -20,9 +20,8 @@
  *                              convolve.cc:26-110
  *   fftwpp_gpu_scale           Convolution{,2,3}::normalize
  *                              convolve.h:1105-1112,1459-1471,1791-1808
- *   fftwpp_gpu_hermitian_*     HermitianSymmetrize{,X,XY} convolve.h:1168-1267
- *   fftwpp_gpu_pack/unpack +   mpitranspose<Complex>::localize0/1
- *   fftwpp_gpu_comm_*          mpi/mpitranspose.h:632-931 (NCCL all-to-all)
+ *   fftwpp_gpu_copy3 +         mpitranspose<Complex>::localize0/1 pack/unpack and
+ *   fftwpp_gpu_comm_*          exchange, mpi/mpitranspose.h:632-931 (NCCL)
  *
  * All functions return 0 on success or a negative FFTWPP_GPU_E* code; the C++
  * layer turns failures into the reference's "message on cerr + exit" policy
@@ -171,6 +170,20 @@ int fftwpp_gpu_scale(double *x, double scale, uint64_t n0, uint64_t n1,
 int fftwpp_gpu_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
                      uint64_t n2, uint64_t d0, uint64_t d1, uint64_t s0,
                      uint64_t s1, void *stream);
+
+/* ---- NCCL exchange for the distributed transpose
+ * (replaces mpi/mpitranspose.h:132-161,632-931) ---- */
+/* 128-byte NCCL unique id: create on one rank, broadcast by any means */
+int fftwpp_gpu_comm_unique_id(char *id128);
+int fftwpp_gpu_comm_create(int rank, int size, const char *id128, void **comm);
+int fftwpp_gpu_comm_destroy(void *comm);
+int fftwpp_gpu_comm_rank(void *comm);
+int fftwpp_gpu_comm_size(void *comm);
+/* MPI_Alltoallv semantics, counts and displacements in BYTES */
+int fftwpp_gpu_comm_alltoallv(void *comm, const void *send,
+                              const uint64_t *scount, const uint64_t *sdispl,
+                              void *recv, const uint64_t *rcount,
+                              const uint64_t *rdispl, void *stream);
 
 #ifdef __cplusplus
 }
