@@ -141,6 +141,26 @@ struct RegFFT {
   static const int NR8=LG/3;
   static const int REM=LG % 3;
 
+  // offset of pass i in the tw8 table and number of table entries
+  static __host__ __device__ constexpr int twOff(int i) {
+    int off=0;
+    for(int k=0; k < i; ++k) off += 7 << (LG-3*(k+1));
+    return off;
+  }
+  static __host__ __device__ constexpr int twCount() {
+    int off=0;
+    for(int k=0; k < NR8; ++k)
+      if(LG-3*(k+1) > 0) off += 7 << (LG-3*(k+1));
+    return off;
+  }
+  template<bool SM>
+  static __device__ __forceinline__ double2 twid(const double2 *tw, int i,
+                                                 int u, int tau) {
+    const int ls=LG-3*(i+1);
+    const double2 *p=tw+twOff(i)+((u-1) << ls)+(tau & ((1 << ls)-1));
+    return SM ? *p : __ldg(p);
+  }
+
   // position of register t of thread tau in a pass whose legs are 2^ls apart
   static __device__ __forceinline__ int pos(int tau, int t, int ls) {
     return ((tau >> ls) << (ls+3))+(tau & ((1 << ls)-1))+(t << ls);
@@ -172,7 +192,7 @@ struct RegFFT {
   }
 
   // in: x[a][t]=W_a[tau+TPT*t]; out: x[a][e]=FFT at scrambled position 8*tau+e
-  template<int NA, class Lay>
+  template<int NA, class Lay, bool SM=false>
   static __device__ __forceinline__ void forward(double2 (&x)[NA][8], int tau,
                                                  const double2 *__restrict__ tw,
                                                  double2 *buf, int bufStride,
@@ -185,7 +205,7 @@ struct RegFFT {
       if(ls > 0) {
 #pragma unroll
         for(int u=1; u < 8; ++u) {
-          const double2 w=__ldg(tw+(7*i+u-1)*TPT+tau);
+          const double2 w=twid<SM>(tw,i,u,tau);
 #pragma unroll
           for(int a=0; a < NA; ++a) x[a][u]=fmul(x[a][u],w);
         }
@@ -209,7 +229,7 @@ struct RegFFT {
   }
 
   // exact adjoint of forward(): in scrambled positions, out x[t]=w[tau+TPT*t]
-  template<int NA, class Lay>
+  template<int NA, class Lay, bool SM=false>
   static __device__ __forceinline__ void adjoint(double2 (&x)[NA][8], int tau,
                                                  const double2 *__restrict__ tw,
                                                  double2 *buf, int bufStride,
@@ -235,7 +255,7 @@ struct RegFFT {
       if(ls > 0) {
 #pragma unroll
         for(int u=1; u < 8; ++u) {
-          const double2 w=__ldg(tw+(7*i+u-1)*TPT+tau);
+          const double2 w=twid<SM>(tw,i,u,tau);
 #pragma unroll
           for(int a=0; a < NA; ++a) x[a][u]=fmulc(x[a][u],w);
         }
@@ -295,116 +315,149 @@ __device__ __forceinline__ double2 toC(double v) {return make_double2(v,0.0);}
 // fused 1-D convolution over contiguous rows (COMPLEX kind, A=2, B=1)
 // ---------------------------------------------------------------------------
 
-template<int LG, int NTERM, int OCC>
-__global__ void __launch_bounds__((1 << LG)/8 > 256 ? (1 << LG)/8 : 256, (1 << LG)/8 > 256 ? 1 : OCC)
+// Persistent CTAs: each loads the twiddle tables (radix-8 twiddles and the
+// residue twiddles zeta^{k0 j} of every sub-block with k0 != 0) into shared
+// memory once and then loops over groups of ROWS rows.  Per row: two padded
+// exchange buffers; the FFTs of the two inputs and the inverse FFT run
+// through buffer 0, the running accumulators rest in buffer 1 meanwhile, so
+// the kernel fits 128 registers (2 CTAs/SM) without local-memory spills.
+template<int LG, int NTERM>
+__global__ void __launch_bounds__((1 << LG)/8 > 256 ? (1 << LG)/8 : 256, (1 << LG)/8 > 256 ? 1 : 2)
 fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                double2 *f0, const double2 *f1, int mult, double scale,
-               long long nrows, long long rs, int tabid)
+               long long nrows, long long rs, int tabid, int zlen,
+               long long ngroups)
 {
   typedef RegFFT<LG> FFT;
   const int M=FFT::N;
   const int TPT=FFT::TPT;
   const int NT=TPT > 256 ? TPT : 256;
   const int ROWS=NT/TPT;
-  // OCC==2 keeps the accumulators in shared memory between sub-blocks so the
-  // kernel fits 128 registers without local-memory spills.
-  const bool PARK=(OCC == 2);
+  const int TWN=FFT::twCount();
+  const int BUF=NTERM*M+NTERM*M/8; // also holds NTERM*M parked accumulators
   extern __shared__ __align__(16) double2 sm[];
+  double2 *tws=sm;
+  double2 *zs=sm+TWN;               // zlen entries per sub-block with k0 != 0
+  int nz=0;
+  for(int isb=0; isb < nsb; ++isb) nz += sbs[isb].k0 != 0;
+  double2 *bufs=zs+(zlen ? (size_t) nz*zlen : 0);
   const int rowInCta=threadIdx.x/TPT;
   const int tau=threadIdx.x % TPT;
-  long long row=(long long) blockIdx.x*ROWS+rowInCta;
-  const bool live=row < nrows;
-  if(!live) row=nrows-1;
-  const int BUF=M+M/8;
-  double2 *buf=sm;                 // two exchange buffers per row
-  double2 *park=sm+2*ROWS*BUF;     // NTERM*M accumulators per row (PARK)
-  RowLayout lay;
-  lay.base=rowInCta*BUF;
-  lay.barid=TPT > 32 ? 1+rowInCta : 0;
-  lay.nthreads=TPT;
-  const int bufStride=ROWS*BUF;
-  const double2 *tw=P.tab[tabid].tw8;
   const int L=P.jmax;
-  double2 *g0=f0+row*rs;
-  const double2 *g1=f1+row*rs;
-  double2 *mypark=park+(size_t) rowInCta*NTERM*M+tau;
 
-  double2 acc[NTERM][8];
-#pragma unroll
-  for(int k=0; k < NTERM; ++k)
-#pragma unroll
-    for(int t=0; t < 8; ++t)
-      acc[k][t]=make_double2(0.0,0.0);
-
-  for(int isb=0; isb < nsb; ++isb) {
-    const long long k0=sbs[isb].k0;
-    if(PARK && isb > 0) {
-#pragma unroll
-      for(int k=0; k < NTERM; ++k)
-#pragma unroll
-        for(int t=0; t < 8; ++t)
-          mypark[(k*8+t)*TPT]=acc[k][t];
-    }
-    double2 x[2][8];
-#pragma unroll
-    for(int t=0; t < 8; ++t) {
-      x[0][t]=make_double2(0.0,0.0);
-      x[1][t]=make_double2(0.0,0.0);
-#pragma unroll
-      for(int k=0; k < NTERM; ++k) {
-        int j=tau+TPT*t+k*M;
-        if(j < L) {
-          double2 a=g0[j];
-          double2 b=g1[j];
-          if(k0 != 0) {
-            double2 z=zeta(P,modN(P,k0,j));
-            a=fmul(a,z);
-            b=fmul(b,z);
-          }
-          x[0][t]=x[0][t]+a;
-          x[1][t]=x[1][t]+b;
-        }
-      }
-    }
-    FFT::template forward<2>(x,tau,tw,buf,bufStride,lay,true);
-    double2 y[1][8];
-    if(mult == FFTWPP_MULT_BINARY) {
-#pragma unroll
-      for(int t=0; t < 8; ++t) y[0][t]=fmul(x[0][t],x[1][t]);
-    } else {
-#pragma unroll
-      for(int t=0; t < 8; ++t) y[0][t]=fmulc(x[0][t],x[1][t]);
-    }
-    FFT::template adjoint<1>(y,tau,tw,buf,bufStride,lay,true);
-    if(PARK && isb > 0) {
-#pragma unroll
-      for(int k=0; k < NTERM; ++k)
-#pragma unroll
-        for(int t=0; t < 8; ++t)
-          acc[k][t]=mypark[(k*8+t)*TPT];
-    }
-#pragma unroll
-    for(int t=0; t < 8; ++t) {
-#pragma unroll
-      for(int k=0; k < NTERM; ++k) {
-        int j=tau+TPT*t+k*M;
-        if(j < L) {
-          double2 v=y[0][t];
-          if(k0 != 0) v=fmulc(v,zeta(P,modN(P,k0,j)));
-          acc[k][t]=acc[k][t]+v;
-        }
+  // tables -> shared memory
+  {
+    const double2 *tw=P.tab[tabid].tw8;
+    for(int i=threadIdx.x; i < TWN; i += NT) tws[i]=__ldg(tw+i);
+    if(zlen) {
+      int slot=0;
+      for(int isb=0; isb < nsb; ++isb) {
+        const long long k0=sbs[isb].k0;
+        if(k0 == 0) continue;
+        for(int j=threadIdx.x; j < zlen; j += NT)
+          zs[(size_t) slot*zlen+j]=zeta(P,modN(P,k0,j));
+        ++slot;
       }
     }
   }
-  if(live) {
+  __syncthreads();
+
+  RowLayout lay;
+  lay.base=rowInCta*2*BUF;
+  lay.barid=TPT > 32 ? 1+rowInCta : 0;
+  lay.nthreads=TPT;
+  double2 *park=bufs+lay.base+BUF+tau;
+
+  for(long long grp=blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    long long row=grp*ROWS+rowInCta;
+    const bool live=row < nrows;
+    if(!live) row=nrows-1;
+    double2 *g0=f0+row*rs;
+    const double2 *g1=f1+row*rs;
+
+    double2 acc[NTERM][8];
 #pragma unroll
     for(int k=0; k < NTERM; ++k)
 #pragma unroll
-      for(int t=0; t < 8; ++t) {
-        int j=tau+TPT*t+k*M;
-        if(j < L)
-          g0[j]=make_double2(acc[k][t].x*scale,acc[k][t].y*scale);
+      for(int t=0; t < 8; ++t)
+        acc[k][t]=make_double2(0.0,0.0);
+
+    int slot=0;
+    for(int isb=0; isb < nsb; ++isb) {
+      const long long k0=sbs[isb].k0;
+      const double2 *zrow=zs+(size_t) slot*zlen;
+      if(k0 != 0) ++slot;
+      if(isb > 0) {
+#pragma unroll
+        for(int k=0; k < NTERM; ++k)
+#pragma unroll
+          for(int t=0; t < 8; ++t)
+            park[(k*8+t)*TPT]=acc[k][t];
       }
+      double2 x[1][8], y[1][8];
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        x[0][t]=make_double2(0.0,0.0);
+        y[0][t]=make_double2(0.0,0.0);
+#pragma unroll
+        for(int k=0; k < NTERM; ++k) {
+          int j=tau+TPT*t+k*M;
+          if(j < L) {
+            double2 a=g0[j];
+            double2 b=g1[j];
+            if(k0 != 0) {
+              double2 z=zlen ? zrow[j] : zeta(P,modN(P,k0,j));
+              a=fmul(a,z);
+              b=fmul(b,z);
+            }
+            x[0][t]=x[0][t]+a;
+            y[0][t]=y[0][t]+b;
+          }
+        }
+      }
+      FFT::template forward<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
+      FFT::template forward<1,RowLayout,true>(y,tau,tws,bufs,0,lay,true);
+      if(mult == FFTWPP_MULT_BINARY) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) x[0][t]=fmul(x[0][t],y[0][t]);
+      } else {
+#pragma unroll
+        for(int t=0; t < 8; ++t) x[0][t]=fmulc(x[0][t],y[0][t]);
+      }
+      FFT::template adjoint<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
+      if(isb > 0) {
+#pragma unroll
+        for(int k=0; k < NTERM; ++k)
+#pragma unroll
+          for(int t=0; t < 8; ++t)
+            acc[k][t]=park[(k*8+t)*TPT];
+      }
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+#pragma unroll
+        for(int k=0; k < NTERM; ++k) {
+          int j=tau+TPT*t+k*M;
+          if(j < L) {
+            double2 v=x[0][t];
+            if(k0 != 0)
+              v=fmulc(v,zlen ? zrow[j] : zeta(P,modN(P,k0,j)));
+            acc[k][t]=acc[k][t]+v;
+          }
+        }
+      }
+    }
+    if(live) {
+#pragma unroll
+      for(int k=0; k < NTERM; ++k)
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          int j=tau+TPT*t+k*M;
+          if(j < L)
+            g0[j]=make_double2(acc[k][t].x*scale,acc[k][t].y*scale);
+        }
+    }
+    // the next group's first exchange starts with a barrier, which also
+    // orders this group's last reads of the exchange buffers
   }
 }
 
@@ -774,17 +827,7 @@ int launchBackwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb,
   return rc ? rc : 1;
 }
 
-int convOcc()
-{
-  static int occ=-1;
-  if(occ < 0) {
-    const char *s=getenv("FFTWPP_CONV_OCC");
-    occ=(s && atoi(s) == 1) ? 1 : 2;
-  }
-  return occ;
-}
-
-template<int NTERM, int OCC>
+template<int NTERM>
 int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
                    uint64_t nrows, uint64_t rs, cudaStream_t st)
 {
@@ -792,22 +835,32 @@ int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
   const int TPT=M/8;
   const int NT=TPT > 256 ? TPT : 256;
   const int ROWS=NT/TPT;
-  size_t smem=2*(size_t) ROWS*(M+M/8)*sizeof(double2);
-  if(OCC == 2) smem += (size_t) ROWS*NTERM*M*sizeof(double2);
+  const int BUF=NTERM*M+NTERM*M/8;
+  int nr8=lg/3, twn=0;
+  for(int k=0; k < nr8; ++k)
+    if(lg-3*(k+1) > 0) twn += 7 << (lg-3*(k+1));
+  int nz=0;
+  for(size_t i=0; i < pl->hsub.size(); ++i) nz += pl->hsub[i].k0 != 0;
+  int zlen=std::min<int>(pl->dev.jmax,NTERM*M);
+  size_t base=(size_t) twn*sizeof(double2)+2*(size_t) ROWS*BUF*sizeof(double2);
+  size_t zbytes=(size_t) nz*zlen*sizeof(double2);
+  const size_t budget=NT > 256 ? SMEM_MAX : 113*1024;
+  if(base+zbytes > budget) {zlen=0; zbytes=0;} // residue twiddles from L1/L2
+  size_t smem=base+zbytes;
   if(smem > SMEM_MAX) return 0;
-  uint64_t grid=(nrows+ROWS-1)/ROWS;
-  if(grid == 0) return 1;
-  if(grid > 0x7fffffffull) return 0;
+  uint64_t ngroups=(nrows+ROWS-1)/ROWS;
+  if(ngroups == 0) return 1;
+  uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) 148*2*4);
   int tabid=0;
   int rc=0;
 #define CALL(LGV)                                                            \
-  rc=allowSmem(fast_conv_rows<LGV,NTERM,OCC>);                               \
+  rc=allowSmem(fast_conv_rows<LGV,NTERM>);                                   \
   if(rc) return rc;                                                          \
   prof_begin(4*pl->tag+2,st);                                                \
-  fast_conv_rows<LGV,NTERM,OCC><<<(unsigned) grid,NT,smem,st>>>              \
+  fast_conv_rows<LGV,NTERM><<<(unsigned) grid,NT,smem,st>>>                  \
     (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],                \
      (const double2 *) f[1],mult,scale,(long long) nrows,(long long) rs,     \
-     tabid);
+     tabid,zlen,(long long) ngroups);
   LG_CASES(CALL)
 #undef CALL
   rc=check_launch("fast_conv_rows",st);
@@ -904,13 +957,9 @@ int fast_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
   if(A != 2 || B != 1) return 0;
   if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
   if(fi->nterm == 1)
-    return convOcc() == 1 ?
-      launchConvRows<1,1>(pl,fi->log2m,f,mult,scale,nrows,rs,st) :
-      launchConvRows<1,2>(pl,fi->log2m,f,mult,scale,nrows,rs,st);
+    return launchConvRows<1>(pl,fi->log2m,f,mult,scale,nrows,rs,st);
   if(fi->nterm == 2)
-    return convOcc() == 1 ?
-      launchConvRows<2,1>(pl,fi->log2m,f,mult,scale,nrows,rs,st) :
-      launchConvRows<2,2>(pl,fi->log2m,f,mult,scale,nrows,rs,st);
+    return launchConvRows<2>(pl,fi->log2m,f,mult,scale,nrows,rs,st);
   return 0;
 }
 

@@ -628,7 +628,9 @@ static int upload_roots(size_t count, size_t period, const double2 **out,
   return FFTWPP_GPU_OK;
 }
 
-// Twiddles of the register radix-8 passes laid out per thread (see FftTab).
+// Twiddles of the register radix-8 passes (see FftTab): pass i (legs 2^ls_i
+// apart, ls_i=lg-3(i+1) > 0) needs omega^{(j*u) 8^i}, j < 2^ls_i, u=1..7,
+// stored at off_i+(u-1)*2^ls_i+j with off_i=7*sum_{k<i} 2^ls_k.
 static int upload_tw8(unsigned n, const double2 **out,
                       std::vector<void *>& owned)
 {
@@ -637,26 +639,26 @@ static int upload_tw8(unsigned n, const double2 **out,
   int lg=0;
   while((1u << lg) < n) ++lg;
   int nr8=lg/3;
-  unsigned tpt=n/8;
-  std::vector<double2> h((size_t) 7*nr8*tpt);
+  std::vector<double2> h;
   const long double twopi=6.283185307179586476925286766559005768L;
   for(int i=0; i < nr8; ++i) {
     int ls=lg-3*(i+1);
+    if(ls <= 0) break;
     for(int u=1; u < 8; ++u)
-      for(unsigned tau=0; tau < tpt; ++tau) {
-        unsigned long long j=tau & ((1u << ls)-1);
-        unsigned long long ph=((j*u) << (3*i)) % n;
+      for(unsigned j=0; j < (1u << ls); ++j) {
+        unsigned long long ph=(((unsigned long long) j*u) << (3*i)) % n;
         long double a=twopi*(long double) ph/(long double) n;
         double2 v;
         v.x=(double) cosl(a);
         v.y=(double) sinl(a);
-        if(4*ph == n) {v.x=0.0; v.y=1.0;}
+        if(ph == 0) {v.x=1.0; v.y=0.0;}
+        else if(4*ph == n) {v.x=0.0; v.y=1.0;}
         else if(2*ph == n) {v.x=-1.0; v.y=0.0;}
         else if(4*ph == 3ull*n) {v.x=0.0; v.y=-1.0;}
-        else if(ph == 0) {v.x=1.0; v.y=0.0;}
-        h[((size_t) 7*i+u-1)*tpt+tau]=v;
+        h.push_back(v);
       }
   }
+  if(h.empty()) return FFTWPP_GPU_OK;
   void *d=NULL;
   cudaError_t e=cudaMalloc(&d,h.size()*sizeof(double2));
   if(e != cudaSuccess) return cuda_fail(e,"cudaMalloc(tw8)");

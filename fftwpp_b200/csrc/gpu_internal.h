@@ -22,9 +22,9 @@ static const int MAXARRAYS=8;  // max(A,B) of a fused convolution
 // Roots of unity and radix schedule of one FFT length.
 struct FftTab {
   const double2 *omega; // omega[k]=exp(2 pi i k/n)
-  // power-of-two lengths: per-thread twiddles of the register radix-8 passes,
-  // tw8[(7*i+u-1)*(n/8)+tau]=omega^{((tau mod 2^ls_i)*u) 8^i}: threads of a
-  // warp read consecutive entries (fast_kernels.cu)
+  // power-of-two lengths: twiddles of the register radix-8 passes; pass i
+  // (ls_i=lg-3(i+1) > 0) at off_i+(u-1)*2^ls_i+j = omega^{(j*u) 8^i},
+  // off_i=7*sum_{k<i} 2^ls_k, so threads of a warp read consecutive entries
   const double2 *tw8;
   int n;
   int nrad;
