@@ -464,6 +464,20 @@ fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
 // ---------------------------------------------------------------------------
 // strided ("Many") forward / backward passes over tiles of T columns
 // ---------------------------------------------------------------------------
+//
+// Persistent CTAs loop over (row, column-tile) work items.  Shared memory:
+//   [tw8 of length M][tw8 of length M/2 (mixed plans)][zeta rows][tile][exchange]
+// DIRECT variants (uniform COMPLEX plans with L <= M): the thread's 8 input
+// points are loaded straight from global memory into registers and reused for
+// every residue; the backward accumulators live in registers too.  Otherwise
+// the input tile / accumulator tile is staged in shared memory (needed when
+// sub-blocks have different lengths: fftPadReal's packed residue class).
+
+struct ManyTables {
+  const double2 *tw[2];  // smem radix-8 twiddles for lengths M and M/2
+  const double2 *zs;     // smem residue twiddles (zlen per sub-block slot)
+  int zlen;
+};
 
 // logical sample j of lane `lane` from the staged tile (lane fastest)
 template<int KIND>
@@ -481,11 +495,22 @@ __device__ __forceinline__ double2 tileInput(const void *in, int j, int jmin,
   return c[(j-jmin)*T+lane];
 }
 
-template<int KIND, int LG>
+__device__ __forceinline__ double2 zetaAt(const PlanDev& P,
+                                          const ManyTables& tb, int slot,
+                                          long long k0, int j)
+{
+  // table rows are indexed by the storage index j-jmin
+  if(tb.zlen) return tb.zs[(size_t) slot*tb.zlen+(j-P.jmin)];
+  return zeta(P,modN(P,k0,j));
+}
+
+template<int KIND, int LG, bool DIRECT>
 __device__ __forceinline__ void forwardSub(const PlanDev& P,
-                                           const SubBlockDev& sb,
-                                           const void *in, double2 *buf,
-                                           void *F,
+                                           const SubBlockDev& sb, int slot,
+                                           const ManyTables& tb, int which,
+                                           const void *in,
+                                           const double2 (&xin)[8],
+                                           double2 *buf, void *F,
                                            long long Fbase, int T, int col0,
                                            bool colsok)
 {
@@ -498,26 +523,36 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
   LaneLayout lay;
   lay.T=T;
   lay.lane=lane;
-  const FftTab& tab=P.tab[sb.tab];
   const long long k0=sb.k0;
   double2 x[1][8];
 #pragma unroll
   for(int t=0; t < 8; ++t) x[0][t]=make_double2(0.0,0.0);
   if(active) {
+    if(DIRECT) {
 #pragma unroll
-    for(int t=0; t < 8; ++t) {
-      int s=tau+TPT*t;
-      int d=(s-P.jmin) & (mlen-1);
-      double2 acc=make_double2(0.0,0.0);
-      for(int j=P.jmin+d; j < P.jmax; j += mlen) {
-        double2 v=tileInput<KIND>(in,j,P.jmin,T,lane);
-        if(k0 != 0) v=fmul(v,zeta(P,modN(P,k0,j)));
-        acc=acc+v;
+      for(int t=0; t < 8; ++t) {
+        int j=tau+TPT*t;
+        double2 v=xin[t];
+        if(k0 != 0 && j < P.jmax) v=fmul(v,zetaAt(P,tb,slot,k0,j));
+        x[0][t]=v;
       }
-      x[0][t]=acc;
+    } else {
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        int s=tau+TPT*t;
+        int d=(s-P.jmin) & (mlen-1);
+        double2 acc=make_double2(0.0,0.0);
+        for(int j=P.jmin+d; j < P.jmax; j += mlen) {
+          double2 v=tileInput<KIND>(in,j,P.jmin,T,lane);
+          if(k0 != 0) v=fmul(v,zetaAt(P,tb,slot,k0,j));
+          acc=acc+v;
+        }
+        x[0][t]=acc;
+      }
     }
   }
-  FFT::template forward<1>(x,active ? tau : 0,tab.tw8,buf,0,lay,active);
+  FFT::template forward<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[which],
+                                           buf,0,lay,active);
   if(active && colsok) {
 #pragma unroll
     for(int e=0; e < 8; ++e) {
@@ -536,45 +571,108 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
   }
 }
 
-template<int KIND, int LG>
+// copy the twiddle tables of a plan into shared memory; returns the first
+// free double2 slot
+template<int LG>
+__device__ __forceinline__ double2 *loadTables(const PlanDev& P,
+                                               const SubBlockDev *sbs,
+                                               int nsb, double2 *sm, int zlen,
+                                               bool mixed, ManyTables& tb)
+{
+  const int M=1 << LG;
+  double2 *p=sm;
+  for(int w=0; w < 2; ++w) {
+    tb.tw[w]=p;
+    if(w == 1 && !mixed) break;
+    const int n=w == 0 ? RegFFT<LG>::twCount() : RegFFT<LG-1>::twCount();
+    const int want=w == 0 ? M : M/2;
+    const double2 *src=NULL;
+    for(int k=0; k < 2; ++k)
+      if(P.tab[k].n == want) src=P.tab[k].tw8;
+    if(src)
+      for(int i=threadIdx.x; i < n; i += blockDim.x) p[i]=__ldg(src+i);
+    p += n;
+  }
+  tb.zs=p;
+  tb.zlen=zlen;
+  if(zlen) {
+    int slot=0;
+    for(int isb=0; isb < nsb; ++isb) {
+      const long long k0=sbs[isb].k0;
+      if(k0 == 0) continue;
+      for(int j=threadIdx.x; j < zlen; j += blockDim.x)
+        p[(size_t) slot*zlen+j]=zeta(P,modN(P,k0,j+P.jmin));
+      ++slot;
+    }
+    p += (size_t) slot*zlen;
+  }
+  return p;
+}
+
+template<int KIND, int LG, bool DIRECT>
 __global__ void __launch_bounds__(512)
 fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                   int layout, const void *f, void *F, long long nrows,
-                  long long frs, long long Frs, int T, int ntc, size_t inbytes)
+                  long long frs, long long Frs, int T, int ntc, size_t inbytes,
+                  int zlen, int mixed, long long ntiles)
 {
   typedef typename Word<KIND>::type word;
-  extern __shared__ __align__(16) unsigned char smraw[];
-  word *in=(word *) smraw;
+  extern __shared__ __align__(16) double2 sm2[];
   const int M=1 << LG;
-  double2 *buf=(double2 *) (smraw+inbytes);
-  const long long row=blockIdx.x/ntc;
-  const int col0=(blockIdx.x % ntc)*T;
+  ManyTables tb;
+  double2 *rest=loadTables<LG>(P,sbs,nsb,sm2,zlen,mixed != 0,tb);
+  word *in=(word *) rest;
+  double2 *buf=(double2 *) ((unsigned char *) rest+inbytes);
   const int lane=threadIdx.x % T;
-  const bool colsok=col0+lane < P.C;
-
-  // stage the input tile: T contiguous words per logical row
-  const word *g=(const word *) f+row*frs+col0;
-  const int total=P.Lin*T;
-  for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
-    int j=idx/T;
-    int c=idx-j*T;
-    in[idx]=(col0+c < P.C) ? g[P.S*j+c] : word();
-  }
+  const int tau=threadIdx.x/T;
   __syncthreads();
 
-  for(int isb=0; isb < nsb; ++isb) {
-    const SubBlockDev sb=sbs[isb];
-    const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
-    if((int) sb.mlen == M)
-      forwardSub<KIND,LG>(P,sb,in,buf,F,Fbase,T,col0,colsok);
-    else
-      forwardSub<KIND,LG-1>(P,sb,in,buf,F,Fbase,T,col0,colsok);
+  for(long long tile=blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row=tile/ntc;
+    const int col0=(int) (tile % ntc)*T;
+    const bool colsok=col0+lane < P.C;
+    const word *g=(const word *) f+row*frs+col0;
+    double2 xin[8];
+    if(DIRECT) {
+      const int TPT=M/8;
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        int j=tau+TPT*t;
+        xin[t]=(colsok && j < P.jmax) ?
+          ((const double2 *) g)[P.S*j+lane] : make_double2(0.0,0.0);
+      }
+    } else {
+      // stage the input tile: T contiguous words per logical row
+      const int total=P.Lin*T;
+      for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
+        int j=idx/T;
+        int c=idx-j*T;
+        in[idx]=(col0+c < P.C) ? g[P.S*j+c] : word();
+      }
+      __syncthreads();
+    }
+    int slot=0;
+    for(int isb=0; isb < nsb; ++isb) {
+      const SubBlockDev sb=sbs[isb];
+      const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
+      const int myslot=slot;
+      if(sb.k0 != 0) ++slot;
+      if((int) sb.mlen == M)
+        forwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,in,xin,buf,F,Fbase,T,
+                                   col0,colsok);
+      else
+        forwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,in,xin,buf,F,Fbase,T,
+                                    col0,colsok);
+    }
+    if(!DIRECT) __syncthreads(); // tile reads done before the next staging
   }
 }
 
-template<int KIND, int LG>
+template<int KIND, int LG, bool DIRECT>
 __device__ __forceinline__ void backwardSub(const PlanDev& P,
-                                            const SubBlockDev& sb, void *acc,
+                                            const SubBlockDev& sb, int slot,
+                                            const ManyTables& tb, int which,
+                                            void *acc, double2 (&racc)[8],
                                             double2 *buf, const void *F,
                                             long long Fbase, int T, int col0,
                                             bool colsok)
@@ -588,7 +686,6 @@ __device__ __forceinline__ void backwardSub(const PlanDev& P,
   LaneLayout lay;
   lay.T=T;
   lay.lane=lane;
-  const FftTab& tab=P.tab[sb.tab];
   const long long k0=sb.k0;
   double2 x[1][8];
 #pragma unroll
@@ -614,69 +711,119 @@ __device__ __forceinline__ void backwardSub(const PlanDev& P,
       x[0][e]=v;
     }
   }
-  FFT::template adjoint<1>(x,active ? tau : 0,tab.tw8,buf,0,lay,active);
+  FFT::template adjoint<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[which],
+                                           buf,0,lay,active);
   if(active) {
-    const int lo=(KIND == FFTWPP_KIND_HERMITIAN) ? 0 : P.jmin;
-    const int shift=(KIND == FFTWPP_KIND_CENTERED) ? P.jmin : 0;
+    if(DIRECT) {
 #pragma unroll
-    for(int t=0; t < 8; ++t) {
-      int s=tau+TPT*t;
-      int d=(s-lo) & (mlen-1);
-      for(int j=lo+d; j < P.jmax; j += mlen) {
+      for(int t=0; t < 8; ++t) {
+        int j=tau+TPT*t;
         double2 v=x[0][t];
-        if(k0 != 0) v=fmulc(v,zeta(P,modN(P,k0,j)));
-        int idx=(j-shift)*T+lane;
-        if(KIND == FFTWPP_KIND_REAL) {
-          double *a=(double *) acc;
-          a[idx] += (sb.flags & FFTWPP_SB_CONJ_OUT) ? v.x : 2.0*v.x;
-        } else {
-          double2 *a=(double2 *) acc;
-          a[idx]=a[idx]+v;
+        if(k0 != 0 && j < P.jmax) v=fmulc(v,zetaAt(P,tb,slot,k0,j));
+        racc[t]=racc[t]+v;
+      }
+    } else {
+      const int lo=(KIND == FFTWPP_KIND_HERMITIAN) ? 0 : P.jmin;
+      const int shift=(KIND == FFTWPP_KIND_CENTERED) ? P.jmin : 0;
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        int s=tau+TPT*t;
+        int d=(s-lo) & (mlen-1);
+        for(int j=lo+d; j < P.jmax; j += mlen) {
+          double2 v=x[0][t];
+          if(k0 != 0) v=fmulc(v,zetaAt(P,tb,slot,k0,j));
+          int idx=(j-shift)*T+lane;
+          if(KIND == FFTWPP_KIND_REAL) {
+            double *a=(double *) acc;
+            a[idx] += (sb.flags & FFTWPP_SB_CONJ_OUT) ? v.x : 2.0*v.x;
+          } else {
+            double2 *a=(double2 *) acc;
+            a[idx]=a[idx]+v;
+          }
         }
       }
     }
   }
-  __syncthreads();
+  if(!DIRECT) __syncthreads();
 }
 
-template<int KIND, int LG>
+template<int KIND, int LG, bool DIRECT>
 __global__ void __launch_bounds__(512)
 fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                    int layout, const void *F, void *f, int accum, double scale,
                    long long nrows, long long Frs, long long frs, int T,
-                   int ntc, size_t accbytes)
+                   int ntc, size_t accbytes, int zlen, int mixed,
+                   long long ntiles)
 {
   typedef typename Word<KIND>::type word;
-  extern __shared__ __align__(16) unsigned char smraw[];
-  word *acc=(word *) smraw;
+  extern __shared__ __align__(16) double2 sm2[];
   const int M=1 << LG;
-  double2 *buf=(double2 *) (smraw+accbytes);
-  const long long row=blockIdx.x/ntc;
-  const int col0=(blockIdx.x % ntc)*T;
+  ManyTables tb;
+  double2 *rest=loadTables<LG>(P,sbs,nsb,sm2,zlen,mixed != 0,tb);
+  word *acc=(word *) rest;
+  double2 *buf=(double2 *) ((unsigned char *) rest+accbytes);
   const int lane=threadIdx.x % T;
-  const bool colsok=col0+lane < P.C;
-  word *g=(word *) f+row*frs+col0;
-  const int total=P.Lin*T;
-  for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
-    int j=idx/T;
-    int c=idx-j*T;
-    acc[idx]=(accum && col0+c < P.C) ? g[P.S*j+c] : word();
-  }
+  const int tau=threadIdx.x/T;
   __syncthreads();
 
-  for(int isb=0; isb < nsb; ++isb) {
-    const SubBlockDev sb=sbs[isb];
-    const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
-    if((int) sb.mlen == M)
-      backwardSub<KIND,LG>(P,sb,acc,buf,F,Fbase,T,col0,colsok);
-    else
-      backwardSub<KIND,LG-1>(P,sb,acc,buf,F,Fbase,T,col0,colsok);
-  }
-  for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
-    int j=idx/T;
-    int c=idx-j*T;
-    if(col0+c < P.C)
-      g[P.S*j+c]=wscale(acc[idx],scale);
+  for(long long tile=blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row=tile/ntc;
+    const int col0=(int) (tile % ntc)*T;
+    const bool colsok=col0+lane < P.C;
+    word *g=(word *) f+row*frs+col0;
+    const int total=P.Lin*T;
+    double2 racc[8];
+#pragma unroll
+    for(int t=0; t < 8; ++t) racc[t]=make_double2(0.0,0.0);
+    if(DIRECT) {
+      if(accum) {
+        const int TPT=M/8;
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          int j=tau+TPT*t;
+          if(colsok && j < P.jmax) racc[t]=((const double2 *) g)[P.S*j+lane];
+        }
+      }
+    } else {
+      for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
+        int j=idx/T;
+        int c=idx-j*T;
+        acc[idx]=(accum && col0+c < P.C) ? g[P.S*j+c] : word();
+      }
+      __syncthreads();
+    }
+    int slot=0;
+    for(int isb=0; isb < nsb; ++isb) {
+      const SubBlockDev sb=sbs[isb];
+      const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
+      const int myslot=slot;
+      if(sb.k0 != 0) ++slot;
+      if((int) sb.mlen == M)
+        backwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,acc,racc,buf,F,Fbase,T,
+                                    col0,colsok);
+      else
+        backwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,acc,racc,buf,F,Fbase,T,
+                                     col0,colsok);
+    }
+    if(DIRECT) {
+      const int TPT=M/8;
+      if(colsok) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          int j=tau+TPT*t;
+          if(j < P.jmax)
+            ((double2 *) g)[P.S*j+lane]=wscale(racc[t],scale);
+        }
+      }
+    } else {
+      for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
+        int j=idx/T;
+        int c=idx-j*T;
+        if(col0+c < P.C)
+          g[P.S*j+c]=wscale(acc[idx],scale);
+      }
+      __syncthreads(); // tile stored before the next tile re-initialises it
+    }
   }
 }
 
@@ -754,38 +901,80 @@ bool fastDisabled()
     default: return 0;            \
   }
 
+struct ManyGeom {
+  int T, nthreads, ntc, zlen, mixed;
+  size_t tilebytes, smem;
+  uint64_t ntiles, grid;
+  bool direct;
+};
+
+// Tile geometry, shared-memory budget and persistent grid of a Many pass.
+template<int KIND>
+int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g)
+{
+  FastInfo *fi=pl->fast;
+  const int M=1 << lg;
+  g.mixed=fi->uniform ? 0 : 1;
+  g.direct=fi->uniform && KIND == FFTWPP_KIND_COMPLEX && fi->nterm == 1;
+  int twn=0;
+  for(int k=0; k < lg/3; ++k)
+    if(lg-3*(k+1) > 0) twn += 7 << (lg-3*(k+1));
+  if(g.mixed)
+    for(int k=0; k < (lg-1)/3; ++k)
+      if(lg-1-3*(k+1) > 0) twn += 7 << (lg-1-3*(k+1));
+  int nz=0;
+  for(size_t i=0; i < pl->hsub.size(); ++i) nz += pl->hsub[i].k0 != 0;
+  int span=pl->dev.jmax-pl->dev.jmin;
+  int T=tileLanes();
+  while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
+  for(;;) {
+    g.tilebytes=g.direct ? 0 :
+      (((size_t) pl->dev.Lin*T*wordBytes(KIND)+15) & ~(size_t) 15);
+    size_t base=(size_t) twn*sizeof(double2)+g.tilebytes+
+      (size_t) M*T*sizeof(double2);
+    size_t zbytes=(size_t) nz*span*sizeof(double2);
+    g.zlen=span;
+    if(zbytes > 48*1024 || base+zbytes > SMEM_MAX) {g.zlen=0; zbytes=0;}
+    g.smem=base+zbytes;
+    if(g.smem <= SMEM_MAX && T*(M/8) <= 512) break;
+    if(T == 1) return 0;
+    T /= 2;
+  }
+  g.T=T;
+  g.nthreads=T*(M/8);
+  if(g.nthreads < 32) return 0;
+  g.ntc=(int) ((pl->dev.C+T-1)/T);
+  g.ntiles=nrows*(uint64_t) g.ntc;
+  // persistent grid: as many CTAs as fit on the device (by shared memory and
+  // threads), a few waves for load balance
+  size_t perSM=std::min<size_t>(std::max<size_t>(1,(227*1024)/(g.smem+1024)),
+                                2048/g.nthreads);
+  g.grid=std::min<uint64_t>(g.ntiles,(uint64_t) 148*perSM*4);
+  return 1;
+}
+
 template<int KIND>
 int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
                       const void *f, void *F, uint64_t nrows, uint64_t frs,
                       uint64_t Frs, cudaStream_t st)
 {
-  int T=tileLanes();
-  while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
-  const int M=1 << lg;
-  size_t inbytes,smem;
-  for(;;) {
-    inbytes=((size_t) pl->dev.Lin*T*wordBytes(KIND)+15) & ~(size_t) 15;
-    smem=inbytes+(size_t) M*T*sizeof(double2);
-    if(smem <= SMEM_MAX && T*(M/8) <= 512) break;
-    if(T == 1) return 0;
-    T /= 2;
-  }
-  int nthreads=T*(M/8);
-  if(nthreads < 32) return 0;
-  int ntc=(int) ((pl->dev.C+T-1)/T);
-  uint64_t grid=nrows*ntc;
-  if(grid == 0) return 1;
-  if(grid > 0x7fffffffull) return 0;
+  ManyGeom g;
+  if(!manyGeometry<KIND>(pl,lg,nrows,g)) return 0;
+  if(g.ntiles == 0) return 1;
+  // zeta rows are indexed by sub-block slot within [sb0,sb0+nsb)
   int rc=0;
-#define CALL(LGV)                                                            \
-  rc=allowSmem(fast_forward_many<KIND,LGV>);                                 \
+#define CALLD(LGV, DIR)                                                      \
+  rc=allowSmem(fast_forward_many<KIND,LGV,DIR>);                             \
   if(rc) return rc;                                                          \
   prof_begin(4*pl->tag+0,st);                                                \
-  fast_forward_many<KIND,LGV><<<(unsigned) grid,nthreads,smem,st>>>          \
+  fast_forward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
     (pl->dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,            \
-     (long long) frs,(long long) Frs,T,ntc,inbytes);
+     (long long) frs,(long long) Frs,g.T,g.ntc,g.tilebytes,g.zlen,g.mixed,   \
+     (long long) g.ntiles);
+#define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
   LG_CASES(CALL)
 #undef CALL
+#undef CALLD
   rc=check_launch("fast_forward_many",st);
   return rc ? rc : 1;
 }
@@ -796,33 +985,22 @@ int launchBackwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb,
                        double scale, uint64_t nrows, uint64_t Frs,
                        uint64_t frs, cudaStream_t st)
 {
-  int T=tileLanes();
-  while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
-  const int M=1 << lg;
-  size_t accbytes,smem;
-  for(;;) {
-    accbytes=((size_t) pl->dev.Lin*T*wordBytes(KIND)+15) & ~(size_t) 15;
-    smem=accbytes+(size_t) M*T*sizeof(double2);
-    if(smem <= SMEM_MAX && T*(M/8) <= 512) break;
-    if(T == 1) return 0;
-    T /= 2;
-  }
-  int nthreads=T*(M/8);
-  if(nthreads < 32) return 0;
-  int ntc=(int) ((pl->dev.C+T-1)/T);
-  uint64_t grid=nrows*ntc;
-  if(grid == 0) return 1;
-  if(grid > 0x7fffffffull) return 0;
+  ManyGeom g;
+  if(!manyGeometry<KIND>(pl,lg,nrows,g)) return 0;
+  if(g.ntiles == 0) return 1;
   int rc=0;
-#define CALL(LGV)                                                            \
-  rc=allowSmem(fast_backward_many<KIND,LGV>);                                \
+#define CALLD(LGV, DIR)                                                      \
+  rc=allowSmem(fast_backward_many<KIND,LGV,DIR>);                            \
   if(rc) return rc;                                                          \
   prof_begin(4*pl->tag+1,st);                                                \
-  fast_backward_many<KIND,LGV><<<(unsigned) grid,nthreads,smem,st>>>         \
+  fast_backward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
     (pl->dev,pl->dsub+sb0,(int) nsb,layout,F,f,accumulate,scale,             \
-     (long long) nrows,(long long) Frs,(long long) frs,T,ntc,accbytes);
+     (long long) nrows,(long long) Frs,(long long) frs,g.T,g.ntc,            \
+     g.tilebytes,g.zlen,g.mixed,(long long) g.ntiles);
+#define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
   LG_CASES(CALL)
 #undef CALL
+#undef CALLD
   rc=check_launch("fast_backward_many",st);
   return rc ? rc : 1;
 }
