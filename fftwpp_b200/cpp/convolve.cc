@@ -215,7 +215,8 @@ fftBase::fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
   ThreadBase(app.threads), L(L), M(M), C(C), S(S == 0 ? C : S), m(0), p(0),
   q(0), n(0), R(0), dr(0), D(0), D0(0), Cm(0), Sm(0), l(0), b(0),
   inplace(false), app(app), centered(centered), overwrite(false),
-  gpuplan(NULL), gputag(0), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL)
+  gpuplan(NULL), gputag(0), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL),
+  twoStage(false), planA(NULL), planB(NULL)
 {
   checkParameters();
 }
@@ -225,7 +226,8 @@ fftBase::fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
   ThreadBase(app.threads), L(L), M(M), C(C), S(S == 0 ? C : S), m(m), p(0),
   q(0), n(0), R(0), dr(0), D(D), D0(0), Cm(0), Sm(0), l(0), b(0),
   inplace(inplace), app(app), centered(centered), overwrite(false),
-  gpuplan(NULL), gputag(0), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL)
+  gpuplan(NULL), gputag(0), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL),
+  twoStage(false), planA(NULL), planB(NULL)
 {
   checkParameters();
   this->app.D=D;
@@ -233,6 +235,8 @@ fftBase::fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
 
 fftBase::~fftBase()
 {
+  if(planA) fftwpp_gpu_plan_destroy(planA);
+  if(planB) fftwpp_gpu_plan_destroy(planB);
   if(gpuplan) fftwpp_gpu_plan_destroy(gpuplan);
   delete subHost;
   if(devIn) fftwpp_gpu_free(devIn);
@@ -382,7 +386,7 @@ void fftBase::choose(bool Explicit)
     cand.push_back(nextfftsize(ceilquotient(M,2)));
     cand.push_back(nextfftsize(M));
     if(C == 1) cand.push_back(ceilpow2(M));
-    for(size_t mi=64; mi < H && mi <= 4096; mi *= 2)
+    for(size_t mi=16; mi < H && mi <= 4096; mi *= 2)
       cand.push_back(mi);
   }
 
@@ -404,10 +408,17 @@ void fftBase::choose(bool Explicit)
     size_t lane=(C == 1 ? (app.A+app.B)*Lin*word+
                  std::max(app.A,app.B)*mc*sizeof(Complex) :
                  Lin*word+mc*sizeof(Complex));
-    if(!mForced && lane > smemBytes) continue;
+    bool inner=qc > 1 && innerEligible(kind(),L,mc,pc,C,S);
+    if(!mForced && !inner && lane > smemBytes) continue;
     double N=(double) mc*qc;
-    double cost=N*(log2((double) mc)+2.0+pc)*(ispow2(mc) ? 1.0 : 2.5);
-    if(pc > 2) cost *= 1.0+0.25*pc;
+    double cost;
+    if(inner) { // two global passes + one fused pass
+      double lm=log2((double) mc), lp=log2((double) pc);
+      cost=N*(lm+lp+8.0+0.25*fabs(lm-lp));
+    } else {
+      cost=N*(log2((double) mc)+2.0+pc)*(ispow2(mc) ? 1.0 : 2.5);
+      if(pc > 2) cost *= 1.0+0.25*pc;
+    }
     if(!found || cost < best) {
       found=true;
       best=cost;
@@ -461,6 +472,70 @@ void fftBase::setTag(int tag)
 {
   gputag=tag;
   if(gpuplan) fftwpp_gpu_plan_set_tag(gpuplan,gputag);
+  if(planA) fftwpp_gpu_plan_set_tag(planA,gputag);
+  if(planB) fftwpp_gpu_plan_set_tag(planB,gputag);
+}
+
+bool fftBase::innerEligible(Kind kind, size_t L, size_t m, size_t p, size_t C,
+                            size_t S)
+{
+  return kind == COMPLEX && C == 1 && S == 1 && p > 2 && ispow2(m) &&
+    ispow2(p) && m >= 16 && m <= 4096 && p >= 16 && p <= 4096 && L == p*m;
+}
+
+// Stage A: the reference's "L'=p, M'=q, m'=p, p'=1, q'=n" transform
+// (convolve.cc:619) along t over the m columns s of f[t*m+s], followed by the
+// outer twiddle zeta_N^{(n*u+r)*s}.
+fftwpp_gpu_plan *fftBase::innerA()
+{
+  if(planA) return planA;
+  std::vector<fftwpp_gpu_subblock> sub(n);
+  for(size_t r=0; r < n; ++r) {
+    memset(&sub[r],0,sizeof(sub[r]));
+    sub[r].mlen=(uint32_t) p;
+    sub[r].nout=(uint32_t) p;
+    sub[r].k0=r;
+    sub[r].off_call=sub[r].off_all=r*p*m;
+  }
+  fftwpp_gpu_pad_desc d;
+  memset(&d,0,sizeof(d));
+  d.kind=FFTWPP_KIND_COMPLEX;
+  d.L=p;
+  d.Lin=p;
+  d.N=q;
+  d.m=p;
+  d.C=m;
+  d.S=m;
+  d.nsub=sub.size();
+  d.sub=sub.data();
+  gpu::check(fftwpp_gpu_plan_create(&d,&planA),"plan creation (inner A)");
+  gpu::check(fftwpp_gpu_plan_set_outer(planA,plan(),n),"outer twiddle");
+  fftwpp_gpu_plan_set_tag(planA,gputag);
+  return planA;
+}
+
+// Stage B: q independent explicit (unpadded) length-m rows.
+fftwpp_gpu_plan *fftBase::innerB()
+{
+  if(planB) return planB;
+  fftwpp_gpu_subblock sb;
+  memset(&sb,0,sizeof(sb));
+  sb.mlen=(uint32_t) m;
+  sb.nout=(uint32_t) m;
+  fftwpp_gpu_pad_desc d;
+  memset(&d,0,sizeof(d));
+  d.kind=FFTWPP_KIND_COMPLEX;
+  d.L=m;
+  d.Lin=m;
+  d.N=m;
+  d.m=m;
+  d.C=1;
+  d.S=1;
+  d.nsub=1;
+  d.sub=&sb;
+  gpu::check(fftwpp_gpu_plan_create(&d,&planB),"plan creation (inner B)");
+  fftwpp_gpu_plan_set_tag(planB,gputag);
+  return planB;
 }
 
 // Host-pointer staging for forward()/backward().
@@ -669,6 +744,7 @@ void fftPad::init()
     }
   }
   buildPlan(sub);
+  twoStage=q > 1 && innerEligible(kind(),L,m,p,C,S);
   report(centered ? "fftPadCentered" : "fftPad");
 }
 
@@ -912,6 +988,27 @@ void Convolution::convolveRows(Complex **f, size_t offset, size_t nrows,
   }
   size_t N=std::max(A,B);
   void *ptrs[16];
+  if(fft->innerFast() && multId != FFTWPP_MULT_NONE) {
+    // two-stage large transform: f -> T (stage A), q rows of length m fused
+    // in T (stage B), T -> f (stage A adjoint, normalisation folded in)
+    size_t q=fft->q, m=fft->m;
+    size_t words=q*m;
+    devT.ensure(N,nrows*words*sizeof(Complex));
+    void *st=gpu::stream();
+    for(size_t a=0; a < A; ++a)
+      gpu::check(fftwpp_gpu_forward(fft->innerA(),0,fft->n,1,f[a]+offset,
+                                    devT.ptr[a],nrows,rowstride,words,st),
+                 "forward (inner A)");
+    for(size_t a=0; a < N; ++a) ptrs[a]=devT.ptr[a];
+    gpu::check(fftwpp_gpu_convolve(fft->innerB(),ptrs,(uint32_t) A,
+                                   (uint32_t) B,multId,1.0,nrows*q,m,st),
+               "convolve (inner B)");
+    for(size_t b=0; b < B; ++b)
+      gpu::check(fftwpp_gpu_backward(fft->innerA(),0,fft->n,1,devT.ptr[b],
+                                     f[b]+offset,0,sc,nrows,words,rowstride,
+                                     st),"backward (inner A)");
+    return;
+  }
   for(size_t a=0; a < N; ++a)
     ptrs[a]=(void *) (f[a]+offset);
   gpu::check(fftwpp_gpu_convolve(fft->plan(),ptrs,(uint32_t) A,(uint32_t) B,

@@ -248,13 +248,25 @@ public:
   size_t allSize() {return totalRows*S;}
   const ResidueCall& call(size_t r);
 
+  // Two-stage ("inner", p > 2) execution of the fused 1-D convolution for
+  // large power-of-two transforms (reference forwardInner/backwardInner,
+  // convolve.cc:1227-1466,1765-1965): stage A = length-p pass over the m
+  // interleaved columns + outer twiddle, stage B = q explicit length-m rows.
+  bool innerFast() {return twoStage;}
+  fftwpp_gpu_plan *innerA();
+  fftwpp_gpu_plan *innerB();
+
 protected:
+  static bool innerEligible(Kind kind, size_t L, size_t m, size_t p, size_t C,
+                            size_t S);
   fftwpp_gpu_plan *gpuplan;
   int gputag;
   std::vector<struct SubBlockHost> *subHost;
   std::vector<ResidueCall> callTable;
   size_t totalRows;
   void *devIn,*devOut; // staging for host-pointer forward()/backward()
+  bool twoStage;
+  fftwpp_gpu_plan *planA,*planB;
 
   fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
           bool centered);
@@ -419,6 +431,7 @@ public:
 protected:
   int multId;
   DeviceArrays dev;
+  DeviceArrays devT; // stage-A output of two-stage transforms
   void run(Complex **f, size_t offset, double scale);
   void runCustom(Complex **f, size_t offset, size_t nrows, size_t rowstride,
                  double scale);

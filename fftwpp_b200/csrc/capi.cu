@@ -162,6 +162,24 @@ int fftwpp_gpu_plan_set_tag(fftwpp_gpu_plan *plan, int tag)
   return 0;
 }
 
+int fftwpp_gpu_plan_set_outer(fftwpp_gpu_plan *child, fftwpp_gpu_plan *parent,
+                              uint64_t n)
+{
+  Plan *c=(Plan *) child;
+  Plan *p=(Plan *) parent;
+  if(!c || !p || n == 0) return FFTWPP_GPU_EINVAL;
+  if(!c->fast || c->dev.C < 2) {
+    set_error("set_outer: the child pass must be a power-of-two strided pass");
+    return FFTWPP_GPU_EUNSUPPORTED;
+  }
+  c->dev.oz1=p->dev.z1;
+  c->dev.oz2=p->dev.z2;
+  c->dev.ozshift=p->dev.zshift;
+  c->dev.on=(long long) n;
+  c->dev.oen=1;
+  return 0;
+}
+
 int fftwpp_gpu_profile_enable(int on) {return prof_enable(on);}
 
 int fftwpp_gpu_profile_read(double *ms, uint64_t *count)
@@ -201,6 +219,10 @@ int fftwpp_gpu_forward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
   rc=fast_try_forward(pl,sb0,nsb,all_layout,f,F,nrows,f_rowstride,
                       F_rowstride,(cudaStream_t) stream);
   if(rc != 0) return rc < 0 ? rc : 0;
+  if(pl->dev.oen) {
+    set_error("forward: outer-twiddle plans need the power-of-two fast path");
+    return FFTWPP_GPU_EUNSUPPORTED;
+  }
   return generic_forward(pl,sb0,nsb,all_layout,f,F,nrows,f_rowstride,
                          F_rowstride,(cudaStream_t) stream);
 }
@@ -217,6 +239,10 @@ int fftwpp_gpu_backward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
   rc=fast_try_backward(pl,sb0,nsb,all_layout,F,f,accumulate,scale,nrows,
                        F_rowstride,f_rowstride,(cudaStream_t) stream);
   if(rc != 0) return rc < 0 ? rc : 0;
+  if(pl->dev.oen) {
+    set_error("backward: outer-twiddle plans need the power-of-two fast path");
+    return FFTWPP_GPU_EUNSUPPORTED;
+  }
   return generic_backward(pl,sb0,nsb,all_layout,F,f,accumulate,scale,nrows,
                           F_rowstride,f_rowstride,(cudaStream_t) stream);
 }

@@ -303,6 +303,15 @@ __device__ __forceinline__ long long modN(const PlanDev& P, long long k0,
   return e < 0 ? e+P.N : e;
 }
 
+// outer twiddle zeta_Nbig^e of a two-stage transform (parent plan's tables)
+__device__ __forceinline__ double2 ozeta(const PlanDev& P, long long e)
+{
+  if(P.ozshift < 0) return __ldg(P.oz1+e);
+  long long hi=e >> P.ozshift;
+  long long lo=e & ((1ll << P.ozshift)-1);
+  return fmul(__ldg(P.oz1+hi),__ldg(P.oz2+lo));
+}
+
 template<int KIND>
 struct Word {typedef double2 type;};
 template<>
@@ -560,6 +569,7 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
       if(l < (int) sb.nout) {
         long long a=Fbase+P.S*l+col0+lane;
         double2 v=x[0][e];
+        if(P.oen) v=fmul(v,ozeta(P,(P.on*l+k0)*(col0+lane)));
         if(KIND == FFTWPP_KIND_HERMITIAN)
           ((double *) F)[a]=v.x;
         else {
@@ -668,14 +678,49 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   }
 }
 
+// Load the 8 scrambled-order points of one transformed sub-block owned by
+// this thread, rebuilding the implied half of r2c (CONJ_OUT) blocks.
+template<int KIND, int LG>
+__device__ __forceinline__ void loadSpectrum(const PlanDev& P,
+                                             const SubBlockDev& sb,
+                                             const void *F, long long Fbase,
+                                             int T, int col0, bool colsok,
+                                             double2 (&x)[8])
+{
+  typedef RegFFT<LG> FFT;
+  const int mlen=FFT::N;
+  const int lane=threadIdx.x % T;
+  const int tau=threadIdx.x/T;
+  const bool active=tau < FFT::TPT;
+#pragma unroll
+  for(int e=0; e < 8; ++e) {
+    double2 v=make_double2(0.0,0.0);
+    if(active && colsok) {
+      int l=FFT::rev(8*tau+e);
+      long long a=Fbase+col0+lane;
+      if(KIND == FFTWPP_KIND_HERMITIAN)
+        v.x=((const double *) F)[a+P.S*l];
+      else if(sb.flags & FFTWPP_SB_CONJ_OUT) {
+        if(l < (int) sb.nout) {
+          v=((const double2 *) F)[a+P.S*l];
+          v.y=-v.y;
+        } else
+          v=((const double2 *) F)[a+P.S*(mlen-l)];
+      } else
+        v=((const double2 *) F)[a+P.S*l];
+      if(P.oen) v=fmulc(v,ozeta(P,(P.on*l+sb.k0)*(col0+lane)));
+    }
+    x[e]=v;
+  }
+}
+
 template<int KIND, int LG, bool DIRECT>
 __device__ __forceinline__ void backwardSub(const PlanDev& P,
                                             const SubBlockDev& sb, int slot,
                                             const ManyTables& tb, int which,
                                             void *acc, double2 (&racc)[8],
-                                            double2 *buf, const void *F,
-                                            long long Fbase, int T, int col0,
-                                            bool colsok)
+                                            double2 *buf,
+                                            const double2 (&xin)[8], int T)
 {
   typedef RegFFT<LG> FFT;
   const int mlen=FFT::N;
@@ -689,28 +734,7 @@ __device__ __forceinline__ void backwardSub(const PlanDev& P,
   const long long k0=sb.k0;
   double2 x[1][8];
 #pragma unroll
-  for(int t=0; t < 8; ++t) x[0][t]=make_double2(0.0,0.0);
-  if(active) {
-#pragma unroll
-    for(int e=0; e < 8; ++e) {
-      int l=FFT::rev(8*tau+e);
-      double2 v=make_double2(0.0,0.0);
-      if(colsok) {
-        long long a=Fbase+col0+lane;
-        if(KIND == FFTWPP_KIND_HERMITIAN)
-          v.x=((const double *) F)[a+P.S*l];
-        else if(sb.flags & FFTWPP_SB_CONJ_OUT) {
-          if(l < (int) sb.nout) {
-            v=((const double2 *) F)[a+P.S*l];
-            v.y=-v.y;
-          } else
-            v=((const double2 *) F)[a+P.S*(mlen-l)];
-        } else
-          v=((const double2 *) F)[a+P.S*l];
-      }
-      x[0][e]=v;
-    }
-  }
+  for(int t=0; t < 8; ++t) x[0][t]=xin[t];
   FFT::template adjoint<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[which],
                                            buf,0,lay,active);
   if(active) {
@@ -793,17 +817,37 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
       __syncthreads();
     }
     int slot=0;
+    double2 xc[8];
+    if(DIRECT) {
+      // software pipeline: the next sub-block's loads are in flight while
+      // the current one is transformed
+      const SubBlockDev s0=sbs[0];
+      loadSpectrum<KIND,LG>(P,s0,F,row*Frs+(layout ? s0.off_all : s0.off_call),
+                            T,col0,colsok,xc);
+    }
     for(int isb=0; isb < nsb; ++isb) {
       const SubBlockDev sb=sbs[isb];
       const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
       const int myslot=slot;
       if(sb.k0 != 0) ++slot;
-      if((int) sb.mlen == M)
-        backwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,acc,racc,buf,F,Fbase,T,
-                                    col0,colsok);
-      else
-        backwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,acc,racc,buf,F,Fbase,T,
-                                     col0,colsok);
+      if(DIRECT) {
+        double2 xn[8];
+        if(isb+1 < nsb) {
+          const SubBlockDev s1=sbs[isb+1];
+          loadSpectrum<KIND,LG>(P,s1,F,
+                                row*Frs+(layout ? s1.off_all : s1.off_call),
+                                T,col0,colsok,xn);
+        }
+        backwardSub<KIND,LG,true>(P,sb,myslot,tb,0,acc,racc,buf,xc,T);
+#pragma unroll
+        for(int t=0; t < 8; ++t) xc[t]=xn[t];
+      } else if((int) sb.mlen == M) {
+        loadSpectrum<KIND,LG>(P,sb,F,Fbase,T,col0,colsok,xc);
+        backwardSub<KIND,LG,false>(P,sb,myslot,tb,0,acc,racc,buf,xc,T);
+      } else {
+        loadSpectrum<KIND,LG-1>(P,sb,F,Fbase,T,col0,colsok,xc);
+        backwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,acc,racc,buf,xc,T);
+      }
     }
     if(DIRECT) {
       const int TPT=M/8;
@@ -926,6 +970,7 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g)
   for(size_t i=0; i < pl->hsub.size(); ++i) nz += pl->hsub[i].k0 != 0;
   int span=pl->dev.jmax-pl->dev.jmin;
   int T=tileLanes();
+  while(T*(M/8) < 256 && T < 128) T *= 2; // short transforms: wider tiles
   while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
   for(;;) {
     g.tilebytes=g.direct ? 0 :

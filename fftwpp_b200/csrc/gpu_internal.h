@@ -55,6 +55,15 @@ struct PlanDev {
   const double2 *z1;
   const double2 *z2;
   FftTab tab[2];
+  // Optional outer twiddle of a two-stage (inner, p > 2) transform: output
+  // row l of sub-block k0, column c is multiplied by zeta_Nbig^{(on*l+k0)*c}
+  // on the way out of a forward pass (conjugate on the way into a backward
+  // pass); oz1/oz2/ozshift are the parent plan's zeta tables.
+  const double2 *oz1;
+  const double2 *oz2;
+  int ozshift;
+  int oen;
+  long long on;
 };
 
 struct ConvPtrs {

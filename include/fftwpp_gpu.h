@@ -123,6 +123,15 @@ uint64_t fftwpp_gpu_launch_count(void);
 int fftwpp_gpu_plan_create(const fftwpp_gpu_pad_desc *desc, fftwpp_gpu_plan **plan);
 int fftwpp_gpu_plan_destroy(fftwpp_gpu_plan *plan);
 
+/* Two-stage ("inner", p > 2; reference fftPad::forwardInner, convolve.cc
+ * :1227-1466) transforms: `child` is the length-p pass over m interleaved
+ * columns; its outputs (row l of sub-block k0, column c) are multiplied by
+ * zeta_N^{(n*l+k0)*c} of `parent` (N = parent padded length) on the way out of
+ * fftwpp_gpu_forward and by the conjugate on the way into fftwpp_gpu_backward.
+ * `parent` must outlive `child`.  Power-of-two strided passes only. */
+int fftwpp_gpu_plan_set_outer(fftwpp_gpu_plan *child, fftwpp_gpu_plan *parent,
+                              uint64_t n);
+
 /* ---- optional per-launch timing with CUDA events on the launch stream ----
  * Plans carry a small tag (0..15) naming the pass they serve (the host classes
  * use 1 = x, 2 = y, 3 = z).  While profiling is enabled every launch is

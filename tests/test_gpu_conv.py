@@ -156,3 +156,45 @@ def test_wrapper_api_matches_generic():
     fp.lib.fftwpp_conv1d_convolve(h, a.ctypes.data, b.ctypes.data)
     fp.lib.fftwpp_conv1d_delete(h)
     assert O.rel_l2(a, want) < 1e-12
+
+
+@pytest.mark.parametrize("L,m", [(256, 16), (1024, 32), (8192, 512), (8192, 128), (65536, 4096)])
+@pytest.mark.parametrize("mult", [2, 3])
+def test_conv1d_two_stage_inner(L, m, mult):
+    """p > 2 with power-of-two m and p: the two-stage pipeline (reference
+    forwardInner/backwardInner, convolve.cc:1227-1466,1765-1965)."""
+    check(fp.FAMILY_COMPLEX, [L], [mult * L], m=[m], D=[1], I=[0], seed=L + m)
+
+
+def test_cfg1_closed_form_full_size():
+    """BASELINE configs[0]: L=2^20, M=2^21 against the exact solution of
+    `hybridconv -a` (tests/hybridconv.cc:50-55,65-69)."""
+    L = 1 << 20
+    f, g, h = O.closed_form_1d(L)
+    conv = fp.HybridConv([L], [2 * L])
+    a = [f.copy(), g.copy()]
+    conv.convolve(a)
+    assert O.rel_l2(a[0], h) < O.tolerance(2 * L)
+    # and against the numpy oracle on seeded random data
+    rng = np.random.default_rng(1234)
+    f, g = crand(rng, L), crand(rng, L)
+    a = [f.copy(), g.copy()]
+    conv.convolve(a)
+    assert O.rel_l2(a[0], O.conv_complex(f, g)) < O.tolerance(2 * L)
+
+
+def test_linearity_large_2d():
+    """Size-independent property at a size the direct sums cannot reach:
+    conv(a f1 + b f2, g) = a conv(f1,g) + b conv(f2,g)."""
+    shape = (1024, 1024)
+    rng = np.random.default_rng(99)
+    f1, f2, g = crand(rng, *shape), crand(rng, *shape), crand(rng, *shape)
+    conv = fp.HybridConv(list(shape), [2 * s for s in shape])
+    outs = []
+    for f in (f1, f2, 2.0 * f1 - 0.5j * f2):
+        a = [np.ascontiguousarray(f.copy()), g.copy()]
+        conv.convolve(a)
+        outs.append(a[0])
+    want = 2.0 * outs[0] - 0.5j * outs[1]
+    assert O.rel_l2(outs[2], want) < 1e-13
+    assert O.rel_l2(outs[0], O.conv_complex(f1, g)) < O.tolerance(2048, 2048)
