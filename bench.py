@@ -287,6 +287,11 @@ def main():
                         "launches_per_step": cnt / args.steps,
                         "model_GB_per_step": b / 1e9,
                         "GBps": (b / 1e9) / (per_step_ms / 1e3) if per_step_ms > 0 else None})
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and L == 512 and world == 1:
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch", {})
     roofline = None
     if kernels:
         k = kernels[0]
@@ -295,7 +300,10 @@ def main():
         achieved = per_launch_bytes / 1e9 / (per_launch_ms / 1e3)
         roofline = {"bound": "hbm", "kernel": "%s-pass %s" % (k["pass"], k["op"]),
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak,
+                    "traffic": traffic.get("%s %s" % (k["pass"], k["op"])),
+                    "traffic_source": "profiles/ncu_traffic.json" if traffic else None,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": per_launch_bytes,
                     "launch_ms": per_launch_ms}
     conv_gbs = total_bytes / max(world, 1) / 1e9 / (ms_per_step / 1e3)

@@ -161,6 +161,15 @@ class HybridConv:
         lib.fftwpp_conv_convolve(self._h, ptrs, 1 if normalized else 0)
         return arrays[0] if self.B == 1 else arrays[:self.B]
 
+    def convolve_rows(self, arrays, nrows, rowstride, normalized=True):
+        """1-D objects: nrows independent convolutions in one batched launch
+        (device tensors shaped (nrows, rowstride))."""
+        n = max(self.A, self.B)
+        ptrs = (ctypes.c_void_p * n)(*[_ptr(a) for a in arrays[:n]])
+        lib.fftwpp_conv_convolve_rows(self._h, ptrs, nrows, rowstride,
+                                      1 if normalized else 0)
+        return arrays[0]
+
 
 PROFILE_OPS = ("forward", "backward", "convolve", "other")
 PROFILE_PASSES = {0: "-", 1: "x", 2: "y", 3: "z"}

@@ -353,6 +353,18 @@ void fftwpp_conv_convolve(void *conv, double **f, int normalized)
   ((Conv *) conv)->convolve((Complex **) f,normalized != 0);
 }
 
+void fftwpp_conv_convolve_rows(void *conv, double **f, size_t nrows,
+                               size_t rowstride, int normalized)
+{
+  Conv *c=(Conv *) conv;
+  if(!c->c1) {
+    std::cerr << "convolve_rows needs a 1-D convolution object" << std::endl;
+    exit(-1);
+  }
+  c->c1->convolveRows((Complex **) f,0,nrows,rowstride,
+                      normalized ? c->c1->scale : 1.0);
+}
+
 void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk)
 {
   Conv *c=(Conv *) conv;

@@ -126,6 +126,12 @@ size_t fftwpp_conv_doubles(void *conv);
 /* f: array of max(A,B) pointers (all host or all device).  normalized != 0:
  * convolve(); else convolveRaw().  Result overwrites f[0..B). */
 void fftwpp_conv_convolve(void *conv, double **f, int normalized);
+/* 1-D objects only: convolve `nrows` independent rows in one batched launch
+ * (row i of array a at f[a]+i*rowstride words; device pointers).  This is what
+ * Convolution2/3 issue for their innermost dimension and what the reference's
+ * OpenMP loop over rows does (convolve.h:1434-1445); BASELINE config 5. */
+void fftwpp_conv_convolve_rows(void *conv, double **f, size_t nrows,
+                               size_t rowstride, int normalized);
 /* batch size (x rows) of the y/z sweep of a 3-D convolution; 0 = all rows */
 void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk);
 
