@@ -1256,6 +1256,15 @@ void Convolution2::convolvePlanes(Complex **F, size_t offset, size_t nplanes,
     }
     convolvey[0]->convolveRows(G.data(),0,np*rows,fftx->S,1.0);
     for(size_t bq=0; bq < B; ++bq) {
+      if(bq < outBase.size() && outBase[bq]) {
+        // offset is in words of F; planes are planestride words apart
+        size_t plane0=(planestride ? offset/planestride : 0)+i0;
+        gpu::check(fftwpp_gpu_backward_mapped(fftx->plan(),0,nsub,devF.ptr[bq],
+                                              outBase[bq],outStride[bq],plane0,
+                                              sc,np,wordsPerPlane,st),
+                   "backward (fused exchange)");
+        continue;
+      }
       char *dst=(char *) (F[bq]+offset)+
         i0*planestride*(real ? sizeof(double) : sizeof(Complex));
       gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[bq],dst,

@@ -23,6 +23,7 @@
 #define FFTWPP_B200_CONVOLVE_H
 
 #include <complex>
+#include <cstdint>
 #include <cstddef>
 #include <cstdlib>
 #include <iostream>
@@ -499,6 +500,13 @@ public:
   // Number of planes processed per batch by convolvePlanes (0 = all).  Small
   // batches keep the y/z intermediates resident in the 126 MB L2.
   size_t planeChunk;
+
+  // Fused exchange (distributed runs): when set, the backward strided pass of
+  // output b stores row j of plane i at (Complex *) outBase[b][j] +
+  // i*outStride[b][j] + column -- possibly in a peer GPU's memory -- instead
+  // of back into F[b] (device arrays; see fftwpp_gpu_backward_mapped).
+  std::vector<const uint64_t *> outBase;
+  std::vector<const int64_t *> outStride;
 
 protected:
   DeviceArrays dev;   // staging of host inputs

@@ -32,76 +32,113 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
   ffty->setTag(2);
   fftz->setTag(3);
   scale=1.0/normalization();
+  commStream=NULL;
+  nchunks=1;
+  const char *e=getenv("FFTWPP_MPI_CHUNKS");
+  if(e && *e) nchunks=std::max<size_t>(1,strtoull(e,NULL,10));
+  // the fused exchange needs both strided passes on the power-of-two
+  // register kernels (fast_kernels.cu) and the y pass in its direct variant
+  auto pow2ok=[](size_t m) {return m >= 64 && m <= 4096 && (m & (m-1)) == 0;};
+  fused=pow2ok(fftx->m) && pow2ok(ffty->m) && ffty->p == 1 &&
+    ffty->kind() == fftBase::COMPLEX && ffty->C >= 4 && fftx->C >= 4 &&
+    fftx->q > 1 && ffty->q > 1 &&
+    (fftx->kind() == fftBase::COMPLEX || fftx->kind() == fftBase::REAL) &&
+    fftx->p <= 2;
+  e=getenv("FFTWPP_MPI_FUSED");
+  if(e && *e == '0') fused=false;
+  fusedReady=false;
 }
 
-Convolution3MPI::~Convolution3MPI() {}
+Convolution3MPI::~Convolution3MPI()
+{
+  for(size_t i=0; i < opened.size(); ++i) fftwpp_gpu_ipc_close(opened[i]);
+  for(size_t i=0; i < events.size(); ++i) fftwpp_gpu_event_destroy(events[i]);
+  if(commStream) fftwpp_gpu_stream_destroy(commStream);
+}
+
+// Sub-range [lo,hi) (relative to the rank's first transformed x row) of
+// chunk c of nc for the given rank.
+void Convolution3MPI::chunkRange(int rank, size_t c, size_t nc, size_t *lo,
+                                 size_t *hi)
+{
+  size_t x=localdimension(d.X,rank,group.size,NULL);
+  *lo=c*x/nc;
+  *hi=(c+1)*x/nc;
+}
 
 // direction 0: x-transformed slab (X x y x Z) -> (x x Y x Z)   [localize1]
 // direction 1: the inverse                                     [localize0]
 void Convolution3MPI::exchangeTable(int direction, uint64_t *scount,
                                     uint64_t *sdispl, uint64_t *rcount,
-                                    uint64_t *rdispl)
+                                    uint64_t *rdispl, size_t c, size_t nc)
 {
   const uint64_t w=sizeof(Complex);
-  uint64_t soff=0, roff=0;
+  uint64_t off=0;
+  size_t mylo,myhi;
+  chunkRange(group.rank,c,nc,&mylo,&myhi);
   for(int p=0; p < group.size; ++p) {
-    size_t px0,py0;
-    size_t px=localdimension(d.X,p,group.size,&px0);
+    size_t px0,py0,plo,phi;
+    localdimension(d.X,p,group.size,&px0);
     size_t py=localdimension(d.Y,p,group.size,&py0);
-    // forward: to p go its x rows of my y slice (contiguous rows of Fx);
-    // from p come my x rows of p's y slice (packed per source)
-    uint64_t toP=(uint64_t) px*d.y*d.Z*w;
-    uint64_t fromP=(uint64_t) d.x*py*d.Z*w;
+    chunkRange(p,c,nc,&plo,&phi);
+    // forward: to p go its chunk rows of my y slice (contiguous rows of Fx);
+    // from p come my chunk rows of p's y slice (packed per source)
+    uint64_t toP=(uint64_t) (phi-plo)*d.y*d.Z*w;
+    uint64_t fromP=(uint64_t) (myhi-mylo)*py*d.Z*w;
+    uint64_t slabOff=(uint64_t) (px0+plo)*d.y*d.Z*w;
     if(direction == 0) {
       scount[p]=toP;
-      sdispl[p]=(uint64_t) px0*d.y*d.Z*w;
+      sdispl[p]=slabOff;
       rcount[p]=fromP;
-      rdispl[p]=roff;
-      roff += fromP;
+      rdispl[p]=off;
     } else {
       scount[p]=fromP;
-      sdispl[p]=soff;
-      soff += fromP;
+      sdispl[p]=off;
       rcount[p]=toP;
-      rdispl[p]=(uint64_t) px0*d.y*d.Z*w;
+      rdispl[p]=slabOff;
     }
+    off += fromP;
   }
 }
 
-void Convolution3MPI::transposeForward(void *Fx, void *T)
+void Convolution3MPI::transposeForward(void *Fx, void *T, size_t c, size_t nc,
+                                       void *st)
 {
   std::vector<uint64_t> sc(group.size),sd(group.size),rc(group.size),
     rd(group.size);
-  exchangeTable(0,sc.data(),sd.data(),rc.data(),rd.data());
-  void *st=gpu::stream();
+  exchangeTable(0,sc.data(),sd.data(),rc.data(),rd.data(),c,nc);
+  size_t lo,hi;
+  chunkRange(group.rank,c,nc,&lo,&hi);
   gpu::check(fftwpp_gpu_comm_alltoallv(group.comm,Fx,sc.data(),sd.data(),
                                        devP.ptr[0],rc.data(),rd.data(),st),
              "all-to-all (localize1)");
-  // unpack: block from p holds [x][py][Z] -> T[x][py0+..][Z]
+  // unpack: block from p holds [rows][py][Z] -> T[lo+..][py0+..][Z]
   for(int p=0; p < group.size; ++p) {
     size_t py0;
     size_t py=localdimension(d.Y,p,group.size,&py0);
-    if(py == 0 || d.x == 0) continue;
-    gpu::check(fftwpp_gpu_copy3((Complex *) T+py0*d.Z,
+    if(py == 0 || hi == lo) continue;
+    gpu::check(fftwpp_gpu_copy3((Complex *) T+lo*d.Y*d.Z+py0*d.Z,
                                 (const char *) devP.ptr[0]+rd[p],
-                                d.x,py,d.Z,d.Y*d.Z,d.Z,py*d.Z,d.Z,st),
+                                hi-lo,py,d.Z,d.Y*d.Z,d.Z,py*d.Z,d.Z,st),
                "unpack");
   }
 }
 
-void Convolution3MPI::transposeBackward(void *T, void *Fx)
+void Convolution3MPI::transposeBackward(void *T, void *Fx, size_t c, size_t nc,
+                                        void *st)
 {
   std::vector<uint64_t> sc(group.size),sd(group.size),rc(group.size),
     rd(group.size);
-  exchangeTable(1,sc.data(),sd.data(),rc.data(),rd.data());
-  void *st=gpu::stream();
+  exchangeTable(1,sc.data(),sd.data(),rc.data(),rd.data(),c,nc);
+  size_t lo,hi;
+  chunkRange(group.rank,c,nc,&lo,&hi);
   for(int p=0; p < group.size; ++p) {
     size_t py0;
     size_t py=localdimension(d.Y,p,group.size,&py0);
-    if(py == 0 || d.x == 0) continue;
+    if(py == 0 || hi == lo) continue;
     gpu::check(fftwpp_gpu_copy3((char *) devP.ptr[0]+sd[p],
-                                (const Complex *) T+py0*d.Z,
-                                d.x,py,d.Z,py*d.Z,d.Z,d.Y*d.Z,d.Z,st),
+                                (const Complex *) T+lo*d.Y*d.Z+py0*d.Z,
+                                hi-lo,py,d.Z,py*d.Z,d.Z,d.Y*d.Z,d.Z,st),
                "pack");
   }
   gpu::check(fftwpp_gpu_comm_alltoallv(group.comm,devP.ptr[0],sc.data(),
@@ -109,6 +146,11 @@ void Convolution3MPI::transposeBackward(void *T, void *Fx)
              "all-to-all (localize0)");
 }
 
+// Pipeline (compute stream C = gpu::stream(), exchange stream X):
+//   C: xfwd(0) xfwd(1) .. | yz(chunk 0) | yz(chunk 1) | ...        | xbwd
+//   X:        F(0,c0) F(1,c0) F(0,c1) F(1,c1) ..  B(c0) B(c1) ..
+// F(a,c): forward exchange + unpack of chunk c of array a; B(c): pack +
+// inverse exchange of chunk c of the outputs.
 void Convolution3MPI::runMPI(Complex **f, size_t offset, double sc)
 {
   size_t N=std::max(A,B);
@@ -125,32 +167,192 @@ void Convolution3MPI::runMPI(Complex **f, size_t offset, double sc)
   devP.ensure(1,std::max(slabWords,tWords)*sizeof(Complex));
   const std::vector<ResidueCall>& calls=fftx->calls();
   size_t nsub=calls.back().sb0+calls.back().nsb;
+  size_t nc=std::max<size_t>(1,nchunks);
+  if(!commStream)
+    gpu::check(fftwpp_gpu_stream_create(&commStream),"stream creation");
+  size_t nev=A+2*nc+2;
+  while(events.size() < nev) {
+    void *ev;
+    gpu::check(fftwpp_gpu_event_create(&ev),"event creation");
+    events.push_back(ev);
+  }
+  void **evX=events.data();          // A: x forward of array a done
+  void **evF=events.data()+A;        // nc: chunk c of every array arrived
+  void **evY=events.data()+A+nc;     // nc: y/z sweep of chunk c done
+  void *evB=events[A+2*nc];          // all inverse exchanges done
+  void *evStart=events[A+2*nc+1];    // previous work on the compute stream
 
   std::vector<Complex *> T(N);
   for(size_t a=0; a < N; ++a) T[a]=(Complex *) devT.ptr[a];
 
+  // the exchange stream must not run ahead of earlier work on the buffers
+  gpu::check(fftwpp_gpu_event_record(evStart,st),"event");
+  gpu::check(fftwpp_gpu_stream_wait_event(commStream,evStart),"wait");
+
   for(size_t a=0; a < A; ++a) {
     gpu::check(fftwpp_gpu_forward(fftx->plan(),0,nsub,1,f[a]+offset,
                                   devF.ptr[a],1,0,0,st),"forward");
-    transposeForward(devF.ptr[a],devT.ptr[a]);
+    gpu::check(fftwpp_gpu_event_record(evX[a],st),"event");
   }
-  if(d.x > 0)
-    convolveyz[0]->convolvePlanes(T.data(),0,d.x,d.Y*d.Z,1.0);
-  for(size_t b=0; b < B; ++b) {
-    transposeBackward(devT.ptr[b],devF.ptr[b]);
+  for(size_t c=0; c < nc; ++c) {
+    for(size_t a=0; a < A; ++a) {
+      if(c == 0)
+        gpu::check(fftwpp_gpu_stream_wait_event(commStream,evX[a]),"wait");
+      transposeForward(devF.ptr[a],devT.ptr[a],c,nc,commStream);
+    }
+    gpu::check(fftwpp_gpu_event_record(evF[c],commStream),"event");
+  }
+  for(size_t c=0; c < nc; ++c) {
+    size_t lo,hi;
+    chunkRange(group.rank,c,nc,&lo,&hi);
+    gpu::check(fftwpp_gpu_stream_wait_event(st,evF[c]),"wait");
+    if(hi > lo)
+      convolveyz[0]->convolvePlanes(T.data(),lo*d.Y*d.Z,hi-lo,d.Y*d.Z,1.0);
+    gpu::check(fftwpp_gpu_event_record(evY[c],st),"event");
+    gpu::check(fftwpp_gpu_stream_wait_event(commStream,evY[c]),"wait");
+    for(size_t b=0; b < B; ++b)
+      transposeBackward(devT.ptr[b],devF.ptr[b],c,nc,commStream);
+  }
+  gpu::check(fftwpp_gpu_event_record(evB,commStream),"event");
+  gpu::check(fftwpp_gpu_stream_wait_event(st,evB),"wait");
+  for(size_t b=0; b < B; ++b)
     gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[b],
                                    f[b]+offset,0,sc,1,0,0,st),"backward");
+}
+
+// One-time collective setup of the fused exchange: allocate the landing
+// buffers, exchange their CUDA IPC handles, map the peers' buffers and build
+// the per-row destination tables of both mapped passes.
+void Convolution3MPI::setupFused()
+{
+  size_t N=std::max(A,B);
+  void *st=gpu::stream();
+  int P=group.size;
+  size_t rows=fftx->allRows();
+  size_t slabWords=rows*fftx->S;               // X x y x Z
+  size_t tWords=std::max<size_t>(d.x,1)*d.Y*d.Z;
+  devF.ensure(N,slabWords*sizeof(Complex));
+  devT.ensure(N,tWords*sizeof(Complex));
+
+  // all-gather the IPC handles of devT[0..N) and devF[0..B)
+  size_t nh=N+B;
+  std::vector<char> mine(64*nh), all(64*nh*P);
+  for(size_t a=0; a < N; ++a)
+    gpu::check(fftwpp_gpu_ipc_get_handle(devT.ptr[a],&mine[64*a]),"ipc handle");
+  for(size_t b=0; b < B; ++b)
+    gpu::check(fftwpp_gpu_ipc_get_handle(devF.ptr[b],&mine[64*(N+b)]),
+               "ipc handle");
+  DeviceArrays tmp;
+  tmp.ensure(2,64*nh*P);
+  gpu::check(fftwpp_gpu_memcpy_h2d(tmp.ptr[0],mine.data(),mine.size(),st),
+             "h2d");
+  gpu::check(fftwpp_gpu_comm_allgather(group.comm,tmp.ptr[0],tmp.ptr[1],64*nh,
+                                       st),"all-gather (ipc handles)");
+  gpu::check(fftwpp_gpu_memcpy_d2h(all.data(),tmp.ptr[1],all.size(),st),"d2h");
+  gpu::check(fftwpp_gpu_stream_sync(st),"sync");
+  peerT.assign((size_t) P*N,NULL);
+  peerF.assign((size_t) P*B,NULL);
+  for(int p=0; p < P; ++p) {
+    for(size_t k=0; k < nh; ++k) {
+      void *ptr=NULL;
+      if(p == group.rank)
+        ptr=k < N ? devT.ptr[k] : devF.ptr[k-N];
+      else {
+        gpu::check(fftwpp_gpu_ipc_open(&all[64*(nh*p+k)],&ptr),"ipc open");
+        opened.push_back(ptr);
+      }
+      if(k < N) peerT[(size_t) p*N+k]=ptr;
+      else peerF[(size_t) p*B+(k-N)]=ptr;
+    }
   }
+
+  // row maps: [A forward maps of X rows][B backward maps of Y rows], each a
+  // base array (uint64) followed by a stride array (int64)
+  size_t fwdLen=d.X, bwdLen=d.Y;
+  size_t words=A*2*fwdLen+B*2*bwdLen;
+  std::vector<uint64_t> host(words);
+  size_t pos=0;
+  const uint64_t w=sizeof(Complex);
+  for(size_t a=0; a < A; ++a) {
+    // x forward: all-layout output row l belongs to the rank owning x row l;
+    // it lands at T_p[(l-x0_p)][y0_me..][:]
+    for(size_t l=0; l < fwdLen; ++l) {
+      int p=(int) std::min<size_t>(l/ceilquotient(d.X,P),P-1);
+      size_t px0;
+      localdimension(d.X,p,P,&px0);
+      host[pos+l]=(uint64_t) peerT[(size_t) p*N+a]+
+        ((l-px0)*d.Y*d.Z+d.y0*d.Z)*w;
+      host[pos+fwdLen+l]=0;
+    }
+    pos += 2*fwdLen;
+  }
+  for(size_t b=0; b < B; ++b) {
+    // y backward: output row j of local plane i (x row x0_me+i) belongs to the
+    // rank owning y row j; it lands at Fx_p[(x0_me+i)][j-y0_p][:]
+    for(size_t j=0; j < bwdLen; ++j) {
+      int p=(int) std::min<size_t>(j/ceilquotient(d.Y,P),P-1);
+      size_t py0;
+      size_t py=localdimension(d.Y,p,P,&py0);
+      host[pos+j]=(uint64_t) peerF[(size_t) p*B+b]+
+        (d.x0*py*d.Z+(j-py0)*d.Z)*w;
+      host[pos+bwdLen+j]=(uint64_t) (int64_t) (py*d.Z);
+    }
+    pos += 2*bwdLen;
+  }
+  devMap.ensure(1,words*sizeof(uint64_t));
+  gpu::check(fftwpp_gpu_memcpy_h2d(devMap.ptr[0],host.data(),
+                                   words*sizeof(uint64_t),st),"h2d");
+  gpu::check(fftwpp_gpu_stream_sync(st),"sync");
+  const uint64_t *base=(const uint64_t *) devMap.ptr[0];
+  convolveyz[0]->outBase.assign(B,NULL);
+  convolveyz[0]->outStride.assign(B,NULL);
+  for(size_t b=0; b < B; ++b) {
+    const uint64_t *m=base+A*2*fwdLen+b*2*bwdLen;
+    convolveyz[0]->outBase[b]=m;
+    convolveyz[0]->outStride[b]=(const int64_t *) (m+bwdLen);
+  }
+  gpu::check(fftwpp_gpu_comm_barrier(group.comm,st),"barrier");
+  fusedReady=true;
+}
+
+// x forward (stores into the peers' transposed buffers) | barrier |
+// y forward, z fused convolution, y backward (stores into the peers' x slabs)
+// | barrier | x backward.
+void Convolution3MPI::runFused(Complex **f, size_t offset, double sc)
+{
+  size_t N=std::max(A,B);
+  void *st=gpu::stream();
+  if(!fusedReady) setupFused();
+  const std::vector<ResidueCall>& calls=fftx->calls();
+  size_t nsub=calls.back().sb0+calls.back().nsb;
+  const uint64_t *base=(const uint64_t *) devMap.ptr[0];
+  for(size_t a=0; a < A; ++a) {
+    const uint64_t *m=base+a*2*d.X;
+    gpu::check(fftwpp_gpu_forward_mapped(fftx->plan(),0,nsub,f[a]+offset,m,
+                                         (const int64_t *) (m+d.X),1,0,st),
+               "forward (fused exchange)");
+  }
+  gpu::check(fftwpp_gpu_comm_barrier(group.comm,st),"barrier");
+  std::vector<Complex *> T(N);
+  for(size_t a=0; a < N; ++a) T[a]=(Complex *) devT.ptr[a];
+  if(d.x > 0)
+    convolveyz[0]->convolvePlanes(T.data(),0,d.x,d.Y*d.Z,1.0);
+  gpu::check(fftwpp_gpu_comm_barrier(group.comm,st),"barrier");
+  for(size_t b=0; b < B; ++b)
+    gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[b],
+                                   f[b]+offset,0,sc,1,0,0,st),"backward");
 }
 
 void Convolution3MPI::convolveRaw(Complex **f, size_t offset, Indices *)
 {
-  runMPI(f,offset,1.0);
+  if(fused) runFused(f,offset,1.0);
+  else runMPI(f,offset,1.0);
 }
 
 void Convolution3MPI::convolve(Complex **f, size_t offset)
 {
-  runMPI(f,offset,scale);
+  if(fused) runFused(f,offset,scale);
+  else runMPI(f,offset,scale);
 }
 
 } // namespace fftwpp

@@ -16,6 +16,7 @@
 #define FFTWPP_B200_MPICONVOLVE_H
 
 #include <cstdint>
+#include <vector>
 
 #include "convolve.h"
 
@@ -75,16 +76,41 @@ public:
   void convolveRaw(Complex **f, size_t offset=0, Indices *indices=NULL);
   void convolve(Complex **f, size_t offset=0);
 
-  // byte counts/displacements of the two exchanges (for tests)
+  // byte counts/displacements of the two exchanges (for tests); chunk c of
+  // nchunks restricts every rank's transformed x rows to its c-th sub-range
   void exchangeTable(int direction, uint64_t *scount, uint64_t *sdispl,
-                     uint64_t *rcount, uint64_t *rdispl);
+                     uint64_t *rcount, uint64_t *rdispl, size_t chunk=0,
+                     size_t nchunks=1);
+
+  // Number of x-row chunks the exchanges are pipelined in (overlap of the
+  // all-to-all with the y/z sweep, cf. mpi/mpiconvolve.h:125-139); env
+  // FFTWPP_MPI_CHUNKS, default 4.
+  size_t nchunks;
+
+  // Fused exchange: the x forward pass and the y backward pass store their
+  // results straight into the owning peer's buffers over NVLink (CUDA IPC
+  // mapped), so there is no send buffer, no pack/unpack pass and no NCCL
+  // copy kernel; NCCL only provides two tiny stream barriers per convolution.
+  // Enabled by default when the passes are on the power-of-two fast path;
+  // env FFTWPP_MPI_FUSED=0 selects the NCCL all-to-all path.
+  bool fused;
 
 protected:
+  bool fusedReady;
+  std::vector<void *> peerT;   // [p*N+a]: peer p's transposed buffer a
+  std::vector<void *> peerF;   // [p*B+b]: peer p's x-slab landing buffer b
+  std::vector<void *> opened;  // IPC mappings to close
+  DeviceArrays devMap;         // row maps (base, stride) per array
+  void setupFused();
+  void runFused(Complex **f, size_t offset, double scale);
   DeviceArrays devT;   // transposed data: x x Y x Z per array
-  DeviceArrays devP;   // pack/unpack staging (one array)
+  DeviceArrays devP;   // pack/unpack staging
+  void *commStream;
+  std::vector<void *> events;
   void runMPI(Complex **f, size_t offset, double scale);
-  void transposeForward(void *Fx, void *T);
-  void transposeBackward(void *T, void *Fx);
+  void chunkRange(int rank, size_t c, size_t nc, size_t *lo, size_t *hi);
+  void transposeForward(void *Fx, void *T, size_t c, size_t nc, void *st);
+  void transposeBackward(void *T, void *Fx, size_t c, size_t nc, void *st);
 };
 
 }

@@ -116,6 +116,56 @@ int fftwpp_gpu_stream_sync(void *stream)
   return 0;
 }
 
+int fftwpp_gpu_stream_create(void **stream)
+{
+  cudaStream_t st;
+  // highest priority: CTAs of the (small) exchange kernels are placed before
+  // queued CTAs of the compute kernels whenever SM resources free up
+  int least=0, greatest=0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least,&greatest),
+           "cudaDeviceGetStreamPriorityRange");
+  CUDA_TRY(cudaStreamCreateWithPriority(&st,cudaStreamNonBlocking,greatest),
+           "cudaStreamCreateWithPriority");
+  *stream=(void *) st;
+  return 0;
+}
+
+int fftwpp_gpu_stream_destroy(void *stream)
+{
+  if(stream) CUDA_TRY(cudaStreamDestroy((cudaStream_t) stream),
+                      "cudaStreamDestroy");
+  return 0;
+}
+
+int fftwpp_gpu_event_create(void **event)
+{
+  cudaEvent_t ev;
+  CUDA_TRY(cudaEventCreateWithFlags(&ev,cudaEventDisableTiming),
+           "cudaEventCreate");
+  *event=(void *) ev;
+  return 0;
+}
+
+int fftwpp_gpu_event_destroy(void *event)
+{
+  if(event) CUDA_TRY(cudaEventDestroy((cudaEvent_t) event),"cudaEventDestroy");
+  return 0;
+}
+
+int fftwpp_gpu_event_record(void *event, void *stream)
+{
+  CUDA_TRY(cudaEventRecord((cudaEvent_t) event,(cudaStream_t) stream),
+           "cudaEventRecord");
+  return 0;
+}
+
+int fftwpp_gpu_stream_wait_event(void *stream, void *event)
+{
+  CUDA_TRY(cudaStreamWaitEvent((cudaStream_t) stream,(cudaEvent_t) event,0),
+           "cudaStreamWaitEvent");
+  return 0;
+}
+
 int fftwpp_gpu_device_sync(void)
 {
   CUDA_TRY(cudaDeviceSynchronize(),"cudaDeviceSynchronize");
@@ -245,6 +295,73 @@ int fftwpp_gpu_backward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
   }
   return generic_backward(pl,sb0,nsb,all_layout,F,f,accumulate,scale,nrows,
                           F_rowstride,f_rowstride,(cudaStream_t) stream);
+}
+
+int fftwpp_gpu_forward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
+                              uint64_t nsb, const void *f,
+                              const uint64_t *rowbase,
+                              const int64_t *rowstride, uint64_t nrows,
+                              uint64_t f_rowstride, void *stream)
+{
+  Plan *pl=(Plan *) plan;
+  int rc=check_range(pl,sb0,nsb);
+  if(rc) return rc;
+  if(!rowbase || !rowstride) return FFTWPP_GPU_EINVAL;
+  rc=fast_try_forward(pl,sb0,nsb,1,f,NULL,nrows,f_rowstride,0,
+                      (cudaStream_t) stream,
+                      (const unsigned long long *) rowbase,
+                      (const long long *) rowstride);
+  if(rc == 0) {
+    set_error("forward_mapped: needs the power-of-two strided fast path");
+    return FFTWPP_GPU_EUNSUPPORTED;
+  }
+  return rc < 0 ? rc : 0;
+}
+
+int fftwpp_gpu_backward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
+                               uint64_t nsb, const void *F,
+                               const uint64_t *rowbase,
+                               const int64_t *rowstride, uint64_t plane0,
+                               double scale, uint64_t nrows,
+                               uint64_t F_rowstride, void *stream)
+{
+  Plan *pl=(Plan *) plan;
+  int rc=check_range(pl,sb0,nsb);
+  if(rc) return rc;
+  if(!rowbase || !rowstride) return FFTWPP_GPU_EINVAL;
+  rc=fast_try_backward(pl,sb0,nsb,1,F,NULL,0,scale,nrows,F_rowstride,0,
+                       (cudaStream_t) stream,
+                       (const unsigned long long *) rowbase,
+                       (const long long *) rowstride,(long long) plane0);
+  if(rc == 0) {
+    set_error("backward_mapped: needs the uniform complex power-of-two fast "
+              "path");
+    return FFTWPP_GPU_EUNSUPPORTED;
+  }
+  return rc < 0 ? rc : 0;
+}
+
+int fftwpp_gpu_ipc_get_handle(void *devptr, char *handle64)
+{
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h,devptr),"cudaIpcGetMemHandle");
+  memcpy(handle64,&h,sizeof(h));
+  return 0;
+}
+
+int fftwpp_gpu_ipc_open(const char *handle64, void **peerptr)
+{
+  cudaIpcMemHandle_t h;
+  memcpy(&h,handle64,sizeof(h));
+  CUDA_TRY(cudaIpcOpenMemHandle(peerptr,h,cudaIpcMemLazyEnablePeerAccess),
+           "cudaIpcOpenMemHandle");
+  return 0;
+}
+
+int fftwpp_gpu_ipc_close(void *peerptr)
+{
+  if(peerptr) CUDA_TRY(cudaIpcCloseMemHandle(peerptr),"cudaIpcCloseMemHandle");
+  return 0;
 }
 
 int fftwpp_gpu_convolve(fftwpp_gpu_plan *plan, void *const *f, uint32_t A,

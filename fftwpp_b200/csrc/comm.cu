@@ -31,6 +31,10 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t,
+                            cudaStream_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t,
+                            cudaStream_t);
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   const char *(*GetErrorString)(ncclResult_t);
@@ -56,6 +60,8 @@ void loadNccl()
   SYM(CommDestroy,"ncclCommDestroy")
   SYM(Send,"ncclSend")
   SYM(Recv,"ncclRecv")
+  SYM(AllReduce,"ncclAllReduce")
+  SYM(AllGather,"ncclAllGather")
   SYM(GroupStart,"ncclGroupStart")
   SYM(GroupEnd,"ncclGroupEnd")
   SYM(GetErrorString,"ncclGetErrorString")
@@ -82,6 +88,7 @@ int ncclFail(ncclResult_t r, const char *what)
 struct Comm {
   ncclComm_t comm;
   int rank, size;
+  int *flag; // device scratch of the stream barrier
 };
 
 } // namespace
@@ -118,6 +125,10 @@ int fftwpp_gpu_comm_create(int rank, int size, const char *id128, void **comm)
     delete c;
     return ncclFail(r,"ncclCommInitRank");
   }
+  c->flag=NULL;
+  cudaError_t e=cudaMalloc((void **) &c->flag,2*sizeof(int));
+  if(e != cudaSuccess) return cuda_fail(e,"cudaMalloc(barrier flag)");
+  cudaMemset(c->flag,0,2*sizeof(int));
   *comm=c;
   return 0;
 }
@@ -127,7 +138,37 @@ int fftwpp_gpu_comm_destroy(void *comm)
   Comm *c=(Comm *) comm;
   if(!c) return 0;
   if(g_nccl.ok) g_nccl.CommDestroy(c->comm);
+  if(c->flag) cudaFree(c->flag);
   delete c;
+  return 0;
+}
+
+// Stream-ordered barrier: work enqueued after it on `stream` starts only
+// after every rank's work enqueued before its own barrier has completed.
+int fftwpp_gpu_comm_barrier(void *comm, void *stream)
+{
+  int rc=needNccl();
+  if(rc) return rc;
+  Comm *c=(Comm *) comm;
+  if(!c) return FFTWPP_GPU_EINVAL;
+  const int ncclInt=2, ncclSum=0;
+  ncclResult_t r=g_nccl.AllReduce(c->flag,c->flag+1,1,ncclInt,ncclSum,c->comm,
+                                  (cudaStream_t) stream);
+  if(r) return ncclFail(r,"ncclAllReduce(barrier)");
+  return 0;
+}
+
+// recv (size*bytes, device) = concatenation of every rank's send (bytes).
+int fftwpp_gpu_comm_allgather(void *comm, const void *send, void *recv,
+                              uint64_t bytes, void *stream)
+{
+  int rc=needNccl();
+  if(rc) return rc;
+  Comm *c=(Comm *) comm;
+  if(!c) return FFTWPP_GPU_EINVAL;
+  ncclResult_t r=g_nccl.AllGather(send,recv,bytes,ncclChar,c->comm,
+                                  (cudaStream_t) stream);
+  if(r) return ncclFail(r,"ncclAllGather");
   return 0;
 }
 

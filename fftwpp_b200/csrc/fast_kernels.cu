@@ -521,7 +521,7 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
                                            const double2 (&xin)[8],
                                            double2 *buf, void *F,
                                            long long Fbase, int T, int col0,
-                                           bool colsok)
+                                           bool colsok, long long plane)
 {
   typedef RegFFT<LG> FFT;
   const int mlen=FFT::N;
@@ -563,6 +563,7 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
   FFT::template forward<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[which],
                                            buf,0,lay,active);
   if(active && colsok) {
+    const long long row0=P.omBase ? sb.off_all/P.S : 0;
 #pragma unroll
     for(int e=0; e < 8; ++e) {
       int l=FFT::rev(8*tau+e);
@@ -574,7 +575,13 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
           ((double *) F)[a]=v.x;
         else {
           if(sb.flags & FFTWPP_SB_CONJ_OUT) v.y=-v.y;
-          ((double2 *) F)[a]=v;
+          if(P.omBase) {
+            // fused exchange: the row goes straight to its owner's buffer
+            double2 *dst=(double2 *) P.omBase[row0+l]+
+              (plane+P.omPlane0)*P.omStride[row0+l]+col0+lane;
+            *dst=v;
+          } else
+            ((double2 *) F)[a]=v;
         }
       }
     }
@@ -669,10 +676,10 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
       if(sb.k0 != 0) ++slot;
       if((int) sb.mlen == M)
         forwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,in,xin,buf,F,Fbase,T,
-                                   col0,colsok);
+                                   col0,colsok,row);
       else
         forwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,in,xin,buf,F,Fbase,T,
-                                    col0,colsok);
+                                    col0,colsok,row);
     }
     if(!DIRECT) __syncthreads(); // tile reads done before the next staging
   }
@@ -855,8 +862,13 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
 #pragma unroll
         for(int t=0; t < 8; ++t) {
           int j=tau+TPT*t;
-          if(j < P.jmax)
-            ((double2 *) g)[P.S*j+lane]=wscale(racc[t],scale);
+          if(j < P.jmax) {
+            if(P.omBase)
+              ((double2 *) P.omBase[j])[(row+P.omPlane0)*P.omStride[j]+col0+lane]=
+                wscale(racc[t],scale);
+            else
+              ((double2 *) g)[P.S*j+lane]=wscale(racc[t],scale);
+          }
         }
       }
     } else {
@@ -1001,11 +1013,17 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g)
 template<int KIND>
 int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
                       const void *f, void *F, uint64_t nrows, uint64_t frs,
-                      uint64_t Frs, cudaStream_t st)
+                      uint64_t Frs, cudaStream_t st,
+                      const unsigned long long *omBase,
+                      const long long *omStride, long long omPlane0)
 {
   ManyGeom g;
   if(!manyGeometry<KIND>(pl,lg,nrows,g)) return 0;
   if(g.ntiles == 0) return 1;
+  PlanDev dev=pl->dev;
+  dev.omBase=omBase;
+  dev.omStride=omStride;
+  dev.omPlane0=omPlane0;
   // zeta rows are indexed by sub-block slot within [sb0,sb0+nsb)
   int rc=0;
 #define CALLD(LGV, DIR)                                                      \
@@ -1013,7 +1031,7 @@ int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
   if(rc) return rc;                                                          \
   prof_begin(4*pl->tag+0,st);                                                \
   fast_forward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
-    (pl->dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,            \
+    (dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,            \
      (long long) frs,(long long) Frs,g.T,g.ntc,g.tilebytes,g.zlen,g.mixed,   \
      (long long) g.ntiles);
 #define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
@@ -1028,18 +1046,25 @@ template<int KIND>
 int launchBackwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb,
                        int layout, const void *F, void *f, int accumulate,
                        double scale, uint64_t nrows, uint64_t Frs,
-                       uint64_t frs, cudaStream_t st)
+                       uint64_t frs, cudaStream_t st,
+                       const unsigned long long *omBase,
+                       const long long *omStride, long long omPlane0)
 {
   ManyGeom g;
   if(!manyGeometry<KIND>(pl,lg,nrows,g)) return 0;
   if(g.ntiles == 0) return 1;
+  if(omBase && !g.direct) return 0; // mapped output: register variant only
+  PlanDev dev=pl->dev;
+  dev.omBase=omBase;
+  dev.omStride=omStride;
+  dev.omPlane0=omPlane0;
   int rc=0;
 #define CALLD(LGV, DIR)                                                      \
   rc=allowSmem(fast_backward_many<KIND,LGV,DIR>);                            \
   if(rc) return rc;                                                          \
   prof_begin(4*pl->tag+1,st);                                                \
   fast_backward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
-    (pl->dev,pl->dsub+sb0,(int) nsb,layout,F,f,accumulate,scale,             \
+    (dev,pl->dsub+sb0,(int) nsb,layout,F,f,accumulate,scale,             \
      (long long) nrows,(long long) Frs,(long long) frs,g.T,g.ntc,            \
      g.tilebytes,g.zlen,g.mixed,(long long) g.ntiles);
 #define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
@@ -1125,7 +1150,9 @@ void fast_plan_free(Plan *pl)
 
 int fast_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                      const void *f, void *F, uint64_t nrows, uint64_t frs,
-                     uint64_t Frs, cudaStream_t st)
+                     uint64_t Frs, cudaStream_t st,
+                     const unsigned long long *omBase,
+                     const long long *omStride, long long omPlane0)
 {
   FastInfo *fi=pl->fast;
   if(!fi || pl->dev.C < 2) return 0;
@@ -1133,13 +1160,16 @@ int fast_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   switch(pl->dev.kind) {
     case FFTWPP_KIND_COMPLEX:
       return launchForwardMany<FFTWPP_KIND_COMPLEX>(pl,lg,sb0,nsb,layout,f,F,
-                                                    nrows,frs,Frs,st);
+                                                    nrows,frs,Frs,st,omBase,
+                                                    omStride,omPlane0);
     case FFTWPP_KIND_CENTERED:
       return launchForwardMany<FFTWPP_KIND_CENTERED>(pl,lg,sb0,nsb,layout,f,F,
-                                                     nrows,frs,Frs,st);
+                                                     nrows,frs,Frs,st,omBase,
+                                                     omStride,omPlane0);
     case FFTWPP_KIND_REAL:
       return launchForwardMany<FFTWPP_KIND_REAL>(pl,lg,sb0,nsb,layout,f,F,
-                                                 nrows,frs,Frs,st);
+                                                 nrows,frs,Frs,st,omBase,
+                                                 omStride,omPlane0);
   }
   return 0;
 }
@@ -1147,7 +1177,8 @@ int fast_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
 int fast_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                       const void *F, void *f, int accumulate, double scale,
                       uint64_t nrows, uint64_t Frs, uint64_t frs,
-                      cudaStream_t st)
+                      cudaStream_t st, const unsigned long long *omBase,
+                      const long long *omStride, long long omPlane0)
 {
   FastInfo *fi=pl->fast;
   if(!fi || pl->dev.C < 2) return 0;
@@ -1156,15 +1187,17 @@ int fast_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
     case FFTWPP_KIND_COMPLEX:
       return launchBackwardMany<FFTWPP_KIND_COMPLEX>(pl,lg,sb0,nsb,layout,F,f,
                                                      accumulate,scale,nrows,
-                                                     Frs,frs,st);
+                                                     Frs,frs,st,omBase,
+                                                     omStride,omPlane0);
     case FFTWPP_KIND_CENTERED:
       return launchBackwardMany<FFTWPP_KIND_CENTERED>(pl,lg,sb0,nsb,layout,F,f,
                                                       accumulate,scale,nrows,
-                                                      Frs,frs,st);
+                                                      Frs,frs,st,omBase,
+                                                      omStride,omPlane0);
     case FFTWPP_KIND_REAL:
       return launchBackwardMany<FFTWPP_KIND_REAL>(pl,lg,sb0,nsb,layout,F,f,
                                                   accumulate,scale,nrows,Frs,
-                                                  frs,st);
+                                                  frs,st,omBase,omStride,omPlane0);
   }
   return 0;
 }

@@ -64,6 +64,12 @@ struct PlanDev {
   int ozshift;
   int oen;
   long long on;
+  // Optional output row map of one launch (fused exchange): output row r of
+  // plane i is written at (word *) omBase[r] + i*omStride[r] + column instead
+  // of the dense layout; omBase entries may be peer-GPU addresses (NVLink).
+  const unsigned long long *omBase;
+  const long long *omStride;
+  long long omPlane0; // plane index of the launch's first row
 };
 
 struct ConvPtrs {
@@ -130,11 +136,15 @@ void fast_plan_init(Plan *pl);
 void fast_plan_free(Plan *pl);
 int fast_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                      const void *f, void *F, uint64_t nrows, uint64_t frs,
-                     uint64_t Frs, cudaStream_t st);
+                     uint64_t Frs, cudaStream_t st,
+                     const unsigned long long *omBase=NULL,
+                     const long long *omStride=NULL, long long omPlane0=0);
 int fast_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                       const void *F, void *f, int accumulate, double scale,
                       uint64_t nrows, uint64_t Frs, uint64_t frs,
-                      cudaStream_t st);
+                      cudaStream_t st,
+                      const unsigned long long *omBase=NULL,
+                      const long long *omStride=NULL, long long omPlane0=0);
 int fast_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
                       int mult, double scale, uint64_t nrows, uint64_t rs,
                       cudaStream_t st);

@@ -112,6 +112,13 @@ int fftwpp_gpu_memcpy2d(void *dst, size_t dpitch, const void *src, size_t spitch
                         size_t width, size_t height, int kind /*0 h2d,1 d2h,2 d2d*/,
                         void *stream);
 int fftwpp_gpu_stream_sync(void *stream);
+/* streams / events for overlapping the exchange with compute */
+int fftwpp_gpu_stream_create(void **stream);
+int fftwpp_gpu_stream_destroy(void *stream);
+int fftwpp_gpu_event_create(void **event);
+int fftwpp_gpu_event_destroy(void *event);
+int fftwpp_gpu_event_record(void *event, void *stream);
+int fftwpp_gpu_stream_wait_event(void *stream, void *event);
 int fftwpp_gpu_device_sync(void);
 /* 1 if ptr is device (or managed) memory, 0 if host, <0 on error */
 int fftwpp_gpu_is_device_ptr(const void *ptr);
@@ -159,6 +166,33 @@ int fftwpp_gpu_backward(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
                         uint64_t nrows, uint64_t F_rowstride,
                         uint64_t f_rowstride, void *stream);
 
+/* Fused exchange (replaces mpitranspose localize1/localize0 + the pack/unpack
+ * passes): the same passes as fftwpp_gpu_forward/backward in the all-residues
+ * layout, but output row r of plane i is stored at
+ *   (word *) rowbase[r] + i*rowstride[r] + column
+ * where rowbase entries may point into PEER GPUs' memory (mapped with
+ * fftwpp_gpu_ipc_open): the transposed data is written over NVLink straight
+ * from the FFT epilogue, tile by tile, overlapping transfer and math.
+ * forward_mapped: r = all-layout output row; backward_mapped: r = input row j
+ * of the transformed dimension, i = plane0 + row index of the batch.
+ * rowbase/rowstride are DEVICE arrays. */
+int fftwpp_gpu_forward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
+                              uint64_t nsb, const void *f,
+                              const uint64_t *rowbase,
+                              const int64_t *rowstride, uint64_t nrows,
+                              uint64_t f_rowstride, void *stream);
+int fftwpp_gpu_backward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
+                               uint64_t nsb, const void *F,
+                               const uint64_t *rowbase,
+                               const int64_t *rowstride, uint64_t plane0,
+                               double scale, uint64_t nrows,
+                               uint64_t F_rowstride, void *stream);
+/* CUDA IPC: export a cudaMalloc'ed buffer / map a peer's buffer (64-byte
+ * handles, exchanged by any means) */
+int fftwpp_gpu_ipc_get_handle(void *devptr, char *handle64);
+int fftwpp_gpu_ipc_open(const char *handle64, void **peerptr);
+int fftwpp_gpu_ipc_close(void *peerptr);
+
 /* Fused 1-D convolution of nrows independent rows (plan must have C==1):
  * for every sub-block, forward all A inputs, apply the multiplier, backward
  * the B outputs and accumulate; padded data never leaves the SM.  The result
@@ -186,6 +220,10 @@ int fftwpp_gpu_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
 int fftwpp_gpu_comm_unique_id(char *id128);
 int fftwpp_gpu_comm_create(int rank, int size, const char *id128, void **comm);
 int fftwpp_gpu_comm_destroy(void *comm);
+/* stream-ordered barrier over all ranks, and byte all-gather */
+int fftwpp_gpu_comm_barrier(void *comm, void *stream);
+int fftwpp_gpu_comm_allgather(void *comm, const void *send, void *recv,
+                              uint64_t bytes, void *stream);
 int fftwpp_gpu_comm_rank(void *comm);
 int fftwpp_gpu_comm_size(void *comm);
 /* MPI_Alltoallv semantics, counts and displacements in BYTES */

@@ -22,7 +22,10 @@ def main():
     fp.lib.fftwpp_gpu_set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for fam, L in ((2, (16, 12, 20)), (2, (33, 9, 8)), (0, (8, 10, 6)), (2, (64, 64, 64))):
+    cases = [(2, (16, 12, 20)), (2, (33, 9, 8)), (0, (8, 10, 6)), (2, (64, 64, 64))]
+    if world > 4:  # every rank needs a non-empty y slab
+        cases = [(2, (16, 8 * world, 12)), (0, (9, 3 * world + 1, 6)), (2, (64, 64, 64))]
+    for fam, L in cases:
         M = [2 * l for l in L]
         c = dist_conv.SlabConvolution3(*L, *M, rank, world, family=fam)
         f = c.make_inputs(seed=7, scale_second=1.0)
