@@ -34,6 +34,8 @@ struct FastInfo {
   int log2m;        // m = 2^log2m: the longer of the (at most two) FFT lengths
   bool uniform;     // every sub-block has length m
   int nterm;        // max number of input terms folded into one W[s]
+  bool pairable;    // REAL plans: every full-length sub-block is an r2c block,
+                    // so two adjacent real columns share one complex FFT
 };
 
 namespace {
@@ -588,6 +590,141 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
   }
 }
 
+// r2c blocks of fftPadReal with two adjacent real columns packed into one
+// complex transform z = x_a + i x_b (reference: rcfftm, convolve.cc:5794,
+// 5881): after the FFT the two spectra are separated with
+//   X_a[l] = (Z[l] + conj Z[M-l])/2,   X_b[l] = (Z[l] - conj Z[M-l])/(2i),
+// the partner Z[M-l] being fetched through shared memory.  T/2 complex lanes.
+template<int LG>
+__device__ __forceinline__ void forwardSubPaired(const PlanDev& P,
+                                                 const SubBlockDev& sb,
+                                                 const ManyTables& tb,
+                                                 const double *in,
+                                                 double2 *buf, void *F,
+                                                 long long Fbase, int T,
+                                                 int col0, long long plane)
+{
+  typedef RegFFT<LG> FFT;
+  const int M=FFT::N;
+  const int TPT=FFT::TPT;
+  const int TL=T/2;
+  const int cl=threadIdx.x % TL;
+  const int tau=threadIdx.x/TL;
+  const bool active=tau < TPT;
+  LaneLayout lay;
+  lay.T=TL;
+  lay.lane=cl;
+  double2 x[1][8];
+#pragma unroll
+  for(int t=0; t < 8; ++t) x[0][t]=make_double2(0.0,0.0);
+  if(active) {
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+      int s=tau+TPT*t;
+      double2 acc=make_double2(0.0,0.0);
+      for(int j=s; j < P.jmax; j += M) {
+        double2 v=((const double2 *) in)[(j*T)/2+cl];
+        acc.x += v.x;
+        acc.y += v.y;
+      }
+      x[0][t]=acc;
+    }
+  }
+  FFT::template forward<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[0],buf,0,
+                                           lay,active);
+  // natural-order copy for the partner lookup
+  __syncthreads();
+  if(active) {
+#pragma unroll
+    for(int e=0; e < 8; ++e) {
+      int l=FFT::rev(8*tau+e);
+      buf[(l+(l >> 3))*TL+cl]=x[0][e];
+    }
+  }
+  __syncthreads();
+  if(active) {
+    const bool oka=col0+2*cl < P.C;
+    const bool okb=col0+2*cl+1 < P.C;
+    const long long row0=P.omBase ? sb.off_all/P.S : 0;
+#pragma unroll
+    for(int e=0; e < 8; ++e) {
+      int l=FFT::rev(8*tau+e);
+      if(l < (int) sb.nout) {
+        double2 z=x[0][e];
+        const int lp=(M-l) & (M-1);
+        double2 zp=buf[(lp+(lp >> 3))*TL+cl];
+        // stored with the r2c (sign -1) convention: conj of the + transform
+        double2 xa=make_double2(0.5*(z.x+zp.x),-0.5*(z.y-zp.y));
+        double2 xb=make_double2(0.5*(z.y+zp.y),0.5*(z.x-zp.x));
+        double2 *dst;
+        if(P.omBase)
+          dst=(double2 *) P.omBase[row0+l]+
+            (plane+P.omPlane0)*P.omStride[row0+l]+col0+2*cl;
+        else
+          dst=(double2 *) F+Fbase+P.S*l+col0+2*cl;
+        if(oka) dst[0]=xa;
+        if(okb) dst[1]=xb;
+      }
+    }
+  }
+}
+
+template<int LG>
+__device__ __forceinline__ void backwardSubPaired(const PlanDev& P,
+                                                  const SubBlockDev& sb,
+                                                  const ManyTables& tb,
+                                                  double *acc, double2 *buf,
+                                                  const void *F,
+                                                  long long Fbase, int T,
+                                                  int col0)
+{
+  typedef RegFFT<LG> FFT;
+  const int M=FFT::N;
+  const int TPT=FFT::TPT;
+  const int TL=T/2;
+  const int cl=threadIdx.x % TL;
+  const int tau=threadIdx.x/TL;
+  const bool active=tau < TPT;
+  LaneLayout lay;
+  lay.T=TL;
+  lay.lane=cl;
+  double2 x[1][8];
+#pragma unroll
+  for(int t=0; t < 8; ++t) x[0][t]=make_double2(0.0,0.0);
+  if(active) {
+    const bool oka=col0+2*cl < P.C;
+    const bool okb=col0+2*cl+1 < P.C;
+    const double2 *src=(const double2 *) F+Fbase+col0+2*cl;
+#pragma unroll
+    for(int e=0; e < 8; ++e) {
+      int l=FFT::rev(8*tau+e);
+      // G[l] of the + transform: conj(stored[l]) for l < nout, else stored[M-l]
+      bool lower=l < (int) sb.nout;
+      const double2 *q=src+P.S*(lower ? l : M-l);
+      double2 ga=oka ? q[0] : make_double2(0.0,0.0);
+      double2 gb=okb ? q[1] : make_double2(0.0,0.0);
+      if(lower) {ga.y=-ga.y; gb.y=-gb.y;}
+      x[0][e]=make_double2(ga.x-gb.y,ga.y+gb.x); // ga + i gb
+    }
+  }
+  FFT::template adjoint<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[0],buf,0,
+                                           lay,active);
+  if(active) {
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+      int s=tau+TPT*t;
+      for(int j=s; j < P.jmax; j += M) {
+        double2 *a=(double2 *) acc+(j*T)/2+cl;
+        double2 v=*a;
+        v.x += x[0][t].x;
+        v.y += x[0][t].y;
+        *a=v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // copy the twiddle tables of a plan into shared memory; returns the first
 // free double2 slot
 template<int LG>
@@ -631,7 +768,7 @@ __global__ void __launch_bounds__(512)
 fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                   int layout, const void *f, void *F, long long nrows,
                   long long frs, long long Frs, int T, int ntc, size_t inbytes,
-                  int zlen, int mixed, long long ntiles)
+                  int zlen, int mixed, long long ntiles, int pair)
 {
   typedef typename Word<KIND>::type word;
   extern __shared__ __align__(16) double2 sm2[];
@@ -674,7 +811,10 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
       const long long Fbase=row*Frs+(layout ? sb.off_all : sb.off_call);
       const int myslot=slot;
       if(sb.k0 != 0) ++slot;
-      if((int) sb.mlen == M)
+      if(KIND == FFTWPP_KIND_REAL && !DIRECT && pair && (int) sb.mlen == M)
+        forwardSubPaired<LG>(P,sb,tb,(const double *) in,buf,F,Fbase,T,col0,
+                             row);
+      else if((int) sb.mlen == M)
         forwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,in,xin,buf,F,Fbase,T,
                                    col0,colsok,row);
       else
@@ -784,7 +924,7 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                    int layout, const void *F, void *f, int accum, double scale,
                    long long nrows, long long Frs, long long frs, int T,
                    int ntc, size_t accbytes, int zlen, int mixed,
-                   long long ntiles)
+                   long long ntiles, int pair)
 {
   typedef typename Word<KIND>::type word;
   extern __shared__ __align__(16) double2 sm2[];
@@ -848,6 +988,8 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
         backwardSub<KIND,LG,true>(P,sb,myslot,tb,0,acc,racc,buf,xc,T);
 #pragma unroll
         for(int t=0; t < 8; ++t) xc[t]=xn[t];
+      } else if(KIND == FFTWPP_KIND_REAL && pair && (int) sb.mlen == M) {
+        backwardSubPaired<LG>(P,sb,tb,(double *) acc,buf,F,Fbase,T,col0);
       } else if((int) sb.mlen == M) {
         loadSpectrum<KIND,LG>(P,sb,F,Fbase,T,col0,colsok,xc);
         backwardSub<KIND,LG,false>(P,sb,myslot,tb,0,acc,racc,buf,xc,T);
@@ -933,6 +1075,16 @@ int tileLanes()
   return T;
 }
 
+bool pairDisabled()
+{
+  static int off=-1;
+  if(off < 0) {
+    const char *s=getenv("FFTWPP_NO_PAIR");
+    off=(s && *s && *s != '0') ? 1 : 0;
+  }
+  return off == 1;
+}
+
 bool fastDisabled()
 {
   static int off=-1;
@@ -958,7 +1110,7 @@ bool fastDisabled()
   }
 
 struct ManyGeom {
-  int T, nthreads, ntc, zlen, mixed;
+  int T, nthreads, ntc, zlen, mixed, pair;
   size_t tilebytes, smem;
   uint64_t ntiles, grid;
   bool direct;
@@ -982,23 +1134,31 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g)
   for(size_t i=0; i < pl->hsub.size(); ++i) nz += pl->hsub[i].k0 != 0;
   int span=pl->dev.jmax-pl->dev.jmin;
   int T=tileLanes();
+  g.pair=(KIND == FFTWPP_KIND_REAL && fi->pairable && pl->dev.C >= 2 &&
+          pl->dev.C % 2 == 0 && pl->dev.S % 2 == 0 && !pairDisabled()) ? 1 : 0;
+  if(g.pair) T *= 2;  // 8-byte words: twice the lanes for the same bytes
   while(T*(M/8) < 256 && T < 128) T *= 2; // short transforms: wider tiles
   while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
+  if(g.pair && T < 2) g.pair=0;
+  const int tdiv=g.pair ? 2 : 1; // threads per lane: M/8, or M/16 when paired
   for(;;) {
     g.tilebytes=g.direct ? 0 :
       (((size_t) pl->dev.Lin*T*wordBytes(KIND)+15) & ~(size_t) 15);
+    // exchange buffer: M points per lane; paired r2c blocks use T/2 complex
+    // lanes plus one padding row per 8 for the natural-order partner lookup
+    size_t bufwords=g.pair ? (size_t) (M+M/8)*(T/2) : (size_t) M*T;
     size_t base=(size_t) twn*sizeof(double2)+g.tilebytes+
-      (size_t) M*T*sizeof(double2);
+      bufwords*sizeof(double2);
     size_t zbytes=(size_t) nz*span*sizeof(double2);
     g.zlen=span;
     if(zbytes > 48*1024 || base+zbytes > SMEM_MAX) {g.zlen=0; zbytes=0;}
     g.smem=base+zbytes;
-    if(g.smem <= SMEM_MAX && T*(M/8) <= 512) break;
-    if(T == 1) return 0;
+    if(g.smem <= SMEM_MAX && T*(M/8)/tdiv <= 512) break;
+    if(T == 1 || (g.pair && T == 2)) return 0;
     T /= 2;
   }
   g.T=T;
-  g.nthreads=T*(M/8);
+  g.nthreads=T*(M/8)/tdiv;
   if(g.nthreads < 32) return 0;
   g.ntc=(int) ((pl->dev.C+T-1)/T);
   g.ntiles=nrows*(uint64_t) g.ntc;
@@ -1033,7 +1193,7 @@ int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
   fast_forward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
     (dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,            \
      (long long) frs,(long long) Frs,g.T,g.ntc,g.tilebytes,g.zlen,g.mixed,   \
-     (long long) g.ntiles);
+     (long long) g.ntiles,g.pair);
 #define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
   LG_CASES(CALL)
 #undef CALL
@@ -1066,7 +1226,7 @@ int launchBackwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb,
   fast_backward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
     (dev,pl->dsub+sb0,(int) nsb,layout,F,f,accumulate,scale,             \
      (long long) nrows,(long long) Frs,(long long) frs,g.T,g.ntc,            \
-     g.tilebytes,g.zlen,g.mixed,(long long) g.ntiles);
+     g.tilebytes,g.zlen,g.mixed,(long long) g.ntiles,g.pair);
 #define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
   LG_CASES(CALL)
 #undef CALL
@@ -1137,6 +1297,17 @@ void fast_plan_init(Plan *pl)
   FastInfo *fi=new FastInfo;
   fi->log2m=ilog2(mmax);
   fi->uniform=uniform;
+  fi->pairable=pl->dev.kind == FFTWPP_KIND_REAL;
+  for(size_t i=0; i < pl->hsub.size(); ++i)
+    if(pl->hsub[i].mlen == mmax && !(pl->hsub[i].flags & FFTWPP_SB_CONJ_OUT))
+      fi->pairable=false;
+  if(!uniform) {
+    // the half-length blocks then use the same thread count as the pairs
+    for(size_t i=0; i < pl->hsub.size(); ++i)
+      if(pl->hsub[i].mlen != mmax &&
+         (pl->hsub[i].flags & FFTWPP_SB_CONJ_OUT))
+        fi->pairable=false;
+  }
   int span=pl->dev.jmax-pl->dev.jmin;
   fi->nterm=(span+(int) mmin-1)/(int) mmin;
   pl->fast=fi;
