@@ -491,19 +491,21 @@ struct ManyTables {
 };
 
 // logical sample j of lane `lane` from the staged tile (lane fastest)
+// rs: words between logical rows (T for the staged tile, the plan stride S
+// when the "tile" is read straight from global memory)
 template<int KIND>
 __device__ __forceinline__ double2 tileInput(const void *in, int j, int jmin,
-                                             int T, int lane)
+                                             long long rs, int lane)
 {
   if(KIND == FFTWPP_KIND_REAL)
-    return make_double2(((const double *) in)[j*T+lane],0.0);
+    return make_double2(((const double *) in)[j*rs+lane],0.0);
   const double2 *c=(const double2 *) in;
   if(KIND == FFTWPP_KIND_HERMITIAN) {
-    if(j >= 0) return c[j*T+lane];
-    double2 v=c[(-j)*T+lane];
+    if(j >= 0) return c[j*rs+lane];
+    double2 v=c[(-j)*rs+lane];
     return make_double2(v.x,-v.y);
   }
-  return c[(j-jmin)*T+lane];
+  return c[(j-jmin)*rs+lane];
 }
 
 __device__ __forceinline__ double2 zetaAt(const PlanDev& P,
@@ -523,7 +525,8 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
                                            const double2 (&xin)[8],
                                            double2 *buf, void *F,
                                            long long Fbase, int T, int col0,
-                                           bool colsok, long long plane)
+                                           bool colsok, long long plane,
+                                           long long rs)
 {
   typedef RegFFT<LG> FFT;
   const int mlen=FFT::N;
@@ -554,7 +557,8 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
         int d=(s-P.jmin) & (mlen-1);
         double2 acc=make_double2(0.0,0.0);
         for(int j=P.jmin+d; j < P.jmax; j += mlen) {
-          double2 v=tileInput<KIND>(in,j,P.jmin,T,lane);
+          double2 v=(rs == T || colsok) ? tileInput<KIND>(in,j,P.jmin,rs,lane)
+            : make_double2(0.0,0.0);
           if(k0 != 0) v=fmul(v,zetaAt(P,tb,slot,k0,j));
           acc=acc+v;
         }
@@ -602,7 +606,8 @@ __device__ __forceinline__ void forwardSubPaired(const PlanDev& P,
                                                  const double *in,
                                                  double2 *buf, void *F,
                                                  long long Fbase, int T,
-                                                 int col0, long long plane)
+                                                 int col0, long long plane,
+                                                 long long rs)
 {
   typedef RegFFT<LG> FFT;
   const int M=FFT::N;
@@ -617,13 +622,14 @@ __device__ __forceinline__ void forwardSubPaired(const PlanDev& P,
   double2 x[1][8];
 #pragma unroll
   for(int t=0; t < 8; ++t) x[0][t]=make_double2(0.0,0.0);
-  if(active) {
+  if(active && (rs == T || col0+2*cl < P.C)) {
+    // C is even in paired mode, so a pair is inside or outside as a whole
 #pragma unroll
     for(int t=0; t < 8; ++t) {
       int s=tau+TPT*t;
       double2 acc=make_double2(0.0,0.0);
       for(int j=s; j < P.jmax; j += M) {
-        double2 v=((const double2 *) in)[(j*T)/2+cl];
+        double2 v=((const double2 *) in)[(j*rs)/2+cl];
         acc.x += v.x;
         acc.y += v.y;
       }
@@ -795,7 +801,7 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
         xin[t]=(colsok && j < P.jmax) ?
           ((const double2 *) g)[P.S*j+lane] : make_double2(0.0,0.0);
       }
-    } else {
+    } else if(inbytes) {
       // stage the input tile: T contiguous words per logical row
       const int total=P.Lin*T;
       for(int idx=threadIdx.x; idx < total; idx += blockDim.x) {
@@ -805,6 +811,9 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
       }
       __syncthreads();
     }
+    // inbytes == 0: every sub-block gathers straight from global memory
+    const void *src=inbytes ? (const void *) in : (const void *) g;
+    const long long rs=inbytes ? T : P.S;
     int slot=0;
     for(int isb=0; isb < nsb; ++isb) {
       const SubBlockDev sb=sbs[isb];
@@ -812,16 +821,16 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
       const int myslot=slot;
       if(sb.k0 != 0) ++slot;
       if(KIND == FFTWPP_KIND_REAL && !DIRECT && pair && (int) sb.mlen == M)
-        forwardSubPaired<LG>(P,sb,tb,(const double *) in,buf,F,Fbase,T,col0,
-                             row);
+        forwardSubPaired<LG>(P,sb,tb,(const double *) src,buf,F,Fbase,T,col0,
+                             row,rs);
       else if((int) sb.mlen == M)
-        forwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,in,xin,buf,F,Fbase,T,
-                                   col0,colsok,row);
+        forwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,src,xin,buf,F,Fbase,T,
+                                   col0,colsok,row,rs);
       else
-        forwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,in,xin,buf,F,Fbase,T,
-                                    col0,colsok,row);
+        forwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,src,xin,buf,F,Fbase,T,
+                                    col0,colsok,row,rs);
     }
-    if(!DIRECT) __syncthreads(); // tile reads done before the next staging
+    if(!DIRECT && inbytes) __syncthreads(); // tile reads done before restaging
   }
 }
 
@@ -1075,6 +1084,16 @@ int tileLanes()
   return T;
 }
 
+bool stageDisabled()
+{
+  static int on=-1;
+  if(on < 0) {
+    const char *s=getenv("FFTWPP_STAGE_REAL");
+    on=(s && *s && *s != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 bool pairDisabled()
 {
   static int off=-1;
@@ -1118,7 +1137,8 @@ struct ManyGeom {
 
 // Tile geometry, shared-memory budget and persistent grid of a Many pass.
 template<int KIND>
-int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g)
+int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g,
+                 bool forward=false)
 {
   FastInfo *fi=pl->fast;
   const int M=1 << lg;
@@ -1142,7 +1162,9 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g)
   if(g.pair && T < 2) g.pair=0;
   const int tdiv=g.pair ? 2 : 1; // threads per lane: M/8, or M/16 when paired
   for(;;) {
-    g.tilebytes=g.direct ? 0 :
+    // forward passes of paired real plans gather straight from global memory
+    const bool notile=g.direct || (forward && g.pair && !stageDisabled());
+    g.tilebytes=notile ? 0 :
       (((size_t) pl->dev.Lin*T*wordBytes(KIND)+15) & ~(size_t) 15);
     // exchange buffer: M points per lane; paired r2c blocks use T/2 complex
     // lanes plus one padding row per 8 for the natural-order partner lookup
@@ -1178,8 +1200,10 @@ int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
                       const long long *omStride, long long omPlane0)
 {
   ManyGeom g;
-  if(!manyGeometry<KIND>(pl,lg,nrows,g)) return 0;
+  if(!manyGeometry<KIND>(pl,lg,nrows,g,true)) return 0;
   if(g.ntiles == 0) return 1;
+  // paired real columns are read as 16-byte words
+  if(g.pair && ((frs & 1) || ((uintptr_t) f & 15))) return 0;
   PlanDev dev=pl->dev;
   dev.omBase=omBase;
   dev.omStride=omStride;
@@ -1213,6 +1237,7 @@ int launchBackwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb,
   ManyGeom g;
   if(!manyGeometry<KIND>(pl,lg,nrows,g)) return 0;
   if(g.ntiles == 0) return 1;
+  if(g.pair && ((frs & 1) || ((uintptr_t) f & 15))) return 0;
   if(omBase && !g.direct) return 0; // mapped output: register variant only
   PlanDev dev=pl->dev;
   dev.omBase=omBase;

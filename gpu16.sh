@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_conv.py tests/test_gpu_golden.py -x -q -m gpu 2>&1 | tail -2
+python -m pytest tests/test_gpu_conv.py tests/test_gpu_golden.py tests/test_gpu_pad.py -x -q -m gpu 2>&1 | tail -2
 python /dev/stdin <<'PY'
 import sys; sys.path.insert(0,'.')
 import numpy as np
@@ -29,10 +29,9 @@ for shape in ((32,32,32),(64,128,32),(128,128,128),(256,16,64),(64,6,5)):
     c=fp.HybridConv(list(shape),[2*s for s in shape],family=fp.FAMILY_REAL); a=[f.copy(),g.copy()]; c.convolve(a); e=O.rel_l2(a[0],O.conv_real(f,g)); print('3dr',shape,e); bad+=e>1e-13
 print('BAD',bad)
 PY
-for pr in 0 1; do
-FFTWPP_NO_PAIR=$((1-pr)) python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e | python -c "
+for st in 1 0; do for T in 4 8; do
+FFTWPP_TILE_LANES=$T FFTWPP_STAGE_REAL=$st python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('pair=$pr',d['value'],'conv/s',d['ms_per_step'],'ms', 'conv frac',d['roofline_conv']['frac'])
-for k in d['kernels']: print('  ',k['pass'],k['op'],round(k['ms_per_step'],3),'ms',k['launches_per_step'],round(k['GBps'] or 0,1),'GB/s')
+d=json.loads(sys.stdin.read()); print('stage=$st T=$T',d['value'],'conv/s',d['ms_per_step'],'ms', {(k['pass'],k['op']):round(k['ms_per_step'],2) for k in d['kernels']})
 "
-done
+done; done
