@@ -472,6 +472,142 @@ fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   }
 }
 
+// Hermitian rows (fftPadHermitian p=2 or explicit; reference forward2/
+// backward2, convolve.cc:4517-4609,4749-4843, with realMultBinary): the input
+// holds the H non-negative modes of a real signal, so every residue's
+//   W[s] = zeta^{k0 s} f[s] + zeta^{k0 (s-m)} conj(f[m-s])
+// is Hermitian in s and its transform is REAL.  The two inputs therefore share
+// ONE complex FFT (Z = W_0 + i W_1 -> X_0 + i X_1), the multiplier is
+// Re(Z)*Im(Z), and one adjoint FFT of that real sequence returns the residue's
+// contribution: 2 FFTs per residue instead of 3.
+template<int LG>
+__global__ void __launch_bounds__((1 << LG)/8 > 256 ? (1 << LG)/8 : 256, (1 << LG)/8 > 256 ? 1 : 2)
+fast_conv_rows_herm(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
+                    double2 *f0, const double2 *f1, double scale,
+                    long long nrows, long long rs, int tabid, int zlen,
+                    long long ngroups)
+{
+  typedef RegFFT<LG> FFT;
+  const int M=FFT::N;
+  const int TPT=FFT::TPT;
+  const int NT=TPT > 256 ? TPT : 256;
+  const int ROWS=NT/TPT;
+  const int TWN=FFT::twCount();
+  const int BUF=M+M/8;
+  extern __shared__ __align__(16) double2 sm[];
+  double2 *tws=sm;
+  double2 *zs=sm+TWN;   // zlen=2H-1 entries (j=-(H-1)..H-1) per k0 != 0 slot
+  int nz=0;
+  for(int isb=0; isb < nsb; ++isb) nz += sbs[isb].k0 != 0;
+  double2 *bufs=zs+(zlen ? (size_t) nz*zlen : 0);
+  const int rowInCta=threadIdx.x/TPT;
+  const int tau=threadIdx.x % TPT;
+  const int H=P.jmax; // stored modes 0..H-1; jmin=-(H-1)
+  {
+    const double2 *tw=P.tab[tabid].tw8;
+    for(int i=threadIdx.x; i < TWN; i += NT) tws[i]=__ldg(tw+i);
+    if(zlen) {
+      int slot=0;
+      for(int isb=0; isb < nsb; ++isb) {
+        const long long k0=sbs[isb].k0;
+        if(k0 == 0) continue;
+        for(int j=threadIdx.x; j < zlen; j += NT)
+          zs[(size_t) slot*zlen+j]=zeta(P,modN(P,k0,j+P.jmin));
+        ++slot;
+      }
+    }
+  }
+  __syncthreads();
+
+  RowLayout lay;
+  lay.base=rowInCta*2*BUF;
+  lay.barid=TPT > 32 ? 1+rowInCta : 0;
+  lay.nthreads=TPT;
+  double2 *park=bufs+lay.base+BUF+tau;
+
+  for(long long grp=blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    long long row=grp*ROWS+rowInCta;
+    const bool live=row < nrows;
+    if(!live) row=nrows-1;
+    double2 *g0=f0+row*rs;
+    const double2 *g1=f1+row*rs;
+
+    double2 acc[8];
+#pragma unroll
+    for(int t=0; t < 8; ++t) acc[t]=make_double2(0.0,0.0);
+
+    int slot=0;
+    for(int isb=0; isb < nsb; ++isb) {
+      const long long k0=sbs[isb].k0;
+      const double2 *zrow=zs+(size_t) slot*zlen-P.jmin; // indexed by j
+      if(k0 != 0) ++slot;
+      if(isb > 0) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) park[t*TPT]=acc[t];
+      }
+      double2 x[1][8];
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        const int s=tau+TPT*t;
+        double2 wa=make_double2(0.0,0.0), wb=make_double2(0.0,0.0);
+        if(s < H) {
+          double2 a=g0[s], b=g1[s];
+          if(s == 0) {a.y=0.0; b.y=0.0;} // c2r ignores Im f[0]
+          if(k0 != 0) {
+            double2 z=zlen ? zrow[s] : zeta(P,modN(P,k0,s));
+            a=fmul(a,z);
+            b=fmul(b,z);
+          }
+          wa=a;
+          wb=b;
+        }
+        const int jn=M-s; // mode -(M-s)
+        if(s >= 1 && jn < H) {
+          double2 a=g0[jn], b=g1[jn];
+          a.y=-a.y;
+          b.y=-b.y;
+          if(k0 != 0) {
+            double2 z=zlen ? zrow[-jn] : zeta(P,modN(P,k0,-jn));
+            a=fmul(a,z);
+            b=fmul(b,z);
+          }
+          wa=wa+a;
+          wb=wb+b;
+        }
+        // Z = W_0 + i W_1
+        x[0][t]=make_double2(wa.x-wb.y,wa.y+wb.x);
+      }
+      FFT::template forward<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        x[0][t]=make_double2(x[0][t].x*x[0][t].y,0.0); // realMultBinary
+      FFT::template adjoint<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
+      if(isb > 0) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) acc[t]=park[t*TPT];
+      }
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        const int s=tau+TPT*t;
+        if(s < H) {
+          double2 v=x[0][t];
+          if(k0 != 0)
+            v=fmulc(v,zlen ? zrow[s] : zeta(P,modN(P,k0,s)));
+          acc[t]=acc[t]+v;
+        }
+      }
+    }
+    if(live) {
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        const int s=tau+TPT*t;
+        if(s < H)
+          g0[s]=make_double2(acc[t].x*scale,acc[t].y*scale);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // strided ("Many") forward / backward passes over tiles of T columns
 // ---------------------------------------------------------------------------
@@ -1300,6 +1436,45 @@ int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
   return rc ? rc : 1;
 }
 
+int launchConvRowsHerm(Plan *pl, int lg, void *const *f, double scale,
+                       uint64_t nrows, uint64_t rs, cudaStream_t st)
+{
+  const int M=1 << lg;
+  const int TPT=M/8;
+  const int NT=TPT > 256 ? TPT : 256;
+  const int ROWS=NT/TPT;
+  const int BUF=M+M/8;
+  int nr8=lg/3, twn=0;
+  for(int k=0; k < nr8; ++k)
+    if(lg-3*(k+1) > 0) twn += 7 << (lg-3*(k+1));
+  int nz=0;
+  for(size_t i=0; i < pl->hsub.size(); ++i) nz += pl->hsub[i].k0 != 0;
+  int zlen=pl->dev.jmax-pl->dev.jmin;
+  size_t base=(size_t) twn*sizeof(double2)+2*(size_t) ROWS*BUF*sizeof(double2);
+  size_t zbytes=(size_t) nz*zlen*sizeof(double2);
+  const size_t budget=NT > 256 ? SMEM_MAX : 113*1024;
+  if(base+zbytes > budget) {zlen=0; zbytes=0;}
+  size_t smem=base+zbytes;
+  if(smem > SMEM_MAX) return 0;
+  uint64_t ngroups=(nrows+ROWS-1)/ROWS;
+  if(ngroups == 0) return 1;
+  uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) 148*2*4);
+  int tabid=0;
+  int rc=0;
+#define CALL(LGV)                                                            \
+  rc=allowSmem(fast_conv_rows_herm<LGV>);                                    \
+  if(rc) return rc;                                                          \
+  prof_begin(4*pl->tag+2,st);                                                \
+  fast_conv_rows_herm<LGV><<<(unsigned) grid,NT,smem,st>>>                   \
+    (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],                \
+     (const double2 *) f[1],scale,(long long) nrows,(long long) rs,tabid,    \
+     zlen,(long long) ngroups);
+  LG_CASES(CALL)
+#undef CALL
+  rc=check_launch("fast_conv_rows_herm",st);
+  return rc ? rc : 1;
+}
+
 } // namespace
 
 void fast_plan_init(Plan *pl)
@@ -1404,9 +1579,16 @@ int fast_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
 {
   FastInfo *fi=pl->fast;
   if(!fi || !fi->uniform) return 0;
-  if(pl->dev.kind != FFTWPP_KIND_COMPLEX || pl->dev.C != 1 || pl->dev.S != 1)
-    return 0;
+  if(pl->dev.C != 1 || pl->dev.S != 1) return 0;
   if(A != 2 || B != 1) return 0;
+  if(pl->dev.kind == FFTWPP_KIND_HERMITIAN) {
+    // stored modes 0..H-1 with H <= m: every W[s] has at most the two terms
+    // j=s and j=s-m
+    if(mult != FFTWPP_MULT_REALBINARY) return 0;
+    if(pl->dev.jmax > (1 << fi->log2m)) return 0;
+    return launchConvRowsHerm(pl,fi->log2m,f,scale,nrows,rs,st);
+  }
+  if(pl->dev.kind != FFTWPP_KIND_COMPLEX) return 0;
   if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
   if(fi->nterm == 1)
     return launchConvRows<1>(pl,fi->log2m,f,mult,scale,nrows,rs,st);

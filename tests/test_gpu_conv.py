@@ -198,3 +198,18 @@ def test_linearity_large_2d():
     want = 2.0 * outs[0] - 0.5j * outs[1]
     assert O.rel_l2(outs[2], want) < 1e-13
     assert O.rel_l2(outs[0], O.conv_complex(f1, g)) < O.tolerance(2048, 2048)
+
+
+@pytest.mark.parametrize("L,M,m", [(32, 48, 16), (256, 384, 128), (256, 512, 128), (1024, 1536, 512),
+                                   (64, 128, 128), (255, 384, 128), (8190, 12288, 4096)])
+def test_conv1d_hermitian_power_of_two(L, M, m):
+    """Hermitian rows on the register kernels (two inputs share one complex
+    FFT; reference forward2/backward2 + realMultBinary, convolve.cc:4517-4843)."""
+    D = 1 if m >= M else 2
+    check(fp.FAMILY_HERMITIAN, [L], [M], m=[m], D=[D], I=[0], seed=L + m)
+
+
+def test_cfg3_shape_hermitian_3d():
+    """BASELINE configs[2] geometry (centred x,y + Hermitian z, M=3L/2) at 64^3."""
+    check(fp.FAMILY_HERMITIAN, (64, 64, 64), None, seed=64)
+    check(fp.FAMILY_HERMITIAN, (128, 32, 256), None, seed=65)
