@@ -24,7 +24,8 @@ def main():
     ok = True
     cases = [(2, (16, 12, 20)), (2, (33, 9, 8)), (0, (8, 10, 6)), (2, (64, 64, 64))]
     if world > 4:  # every rank needs a non-empty y slab
-        cases = [(2, (16, 8 * world, 12)), (0, (9, 3 * world + 1, 6)), (2, (64, 64, 64))]
+        # uneven but non-empty slabs: Ly = 3*(world-1)+1 gives ceil-split 3,...,3,1
+        cases = [(2, (16, 8 * world, 12)), (0, (9, 3 * (world - 1) + 1, 6)), (2, (64, 64, 64))]
     for fam, L in cases:
         M = [2 * l for l in L]
         c = dist_conv.SlabConvolution3(*L, *M, rank, world, family=fam)
