@@ -385,6 +385,17 @@ fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
     if(!live) row=nrows-1;
     double2 *g0=f0+row*rs;
     const double2 *g1=f1+row*rs;
+    if(P.C == 1) { // (always) pull the next group's rows into L2 ahead of use
+      long long nrow=(grp+gridDim.x)*ROWS+rowInCta;
+      if(nrow < nrows) {
+        const char *n0=(const char *) (f0+nrow*rs);
+        const char *n1=(const char *) (f1+nrow*rs);
+        for(int off=tau*128; off < L*16; off += TPT*128) {
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(n0+off));
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(n1+off));
+        }
+      }
+    }
 
     double2 acc[NTERM][8];
 #pragma unroll
@@ -928,6 +939,15 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
     const int col0=(int) (tile % ntc)*T;
     const bool colsok=col0+lane < P.C;
     const word *g=(const word *) f+row*frs+col0;
+    {
+      // pull the next tile's input rows into L2 ahead of use
+      const long long nt=tile+gridDim.x;
+      if(nt < ntiles) {
+        const word *ng=(const word *) f+(nt/ntc)*frs+(int) (nt % ntc)*T;
+        for(int j=threadIdx.x; j < P.Lin; j += blockDim.x)
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(ng+P.S*j));
+      }
+    }
     double2 xin[8];
     if(DIRECT) {
       const int TPT=M/8;
@@ -1088,6 +1108,21 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
     const bool colsok=col0+lane < P.C;
     word *g=(word *) f+row*frs+col0;
     const int total=P.Lin*T;
+    {
+      const long long nt=tile+gridDim.x;
+      if(nt < ntiles && KIND != FFTWPP_KIND_HERMITIAN) {
+        const long long nrow=nt/ntc;
+        const int ncol=(int) (nt % ntc)*T;
+        for(int isb=0; isb < nsb; ++isb) {
+          const long long nb=nrow*Frs+(layout ? sbs[isb].off_all
+                                       : sbs[isb].off_call)+ncol;
+          const int nout=(int) sbs[isb].nout;
+          for(int l=threadIdx.x; l < nout; l += blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" ::
+                         "l"((const double2 *) F+nb+P.S*l));
+        }
+      }
+    }
     double2 racc[8];
 #pragma unroll
     for(int t=0; t < 8; ++t) racc[t]=make_double2(0.0,0.0);
@@ -1220,6 +1255,17 @@ int tileLanes()
   return T;
 }
 
+int realLanes()
+{
+  static int T=-1;
+  if(T < 0) {
+    const char *s=getenv("FFTWPP_TILE_LANES_REAL");
+    T=s ? atoi(s) : 2*tileLanes();
+    if(T != 4 && T != 8 && T != 16 && T != 32) T=2*tileLanes();
+  }
+  return T;
+}
+
 bool stageDisabled()
 {
   static int on=-1;
@@ -1292,7 +1338,7 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g,
   int T=tileLanes();
   g.pair=(KIND == FFTWPP_KIND_REAL && fi->pairable && pl->dev.C >= 2 &&
           pl->dev.C % 2 == 0 && pl->dev.S % 2 == 0 && !pairDisabled()) ? 1 : 0;
-  if(g.pair) T *= 2;  // 8-byte words: twice the lanes for the same bytes
+  if(g.pair) T=realLanes(); // 8-byte words: more lanes for the same bytes
   while(T*(M/8) < 256 && T < 128) T *= 2; // short transforms: wider tiles
   while(T > 1 && (size_t) T > pl->dev.C) T /= 2;
   if(g.pair && T < 2) g.pair=0;
