@@ -168,14 +168,22 @@ struct RegFFT {
     return ((tau >> ls) << (ls+3))+(tau & ((1 << ls)-1))+(t << ls);
   }
 
-  // Array a uses buffer buf+a*bufStride.  Barrier before the writes protects
-  // the previous readers of the buffer, barrier after publishes the writes.
-  template<int NA, class Lay>
+  // Array a uses buffer buf+a*bufStride.  Default: barrier before the writes
+  // (protects the previous readers) and after (publishes).  With PP the
+  // exchanges alternate between two buffers ppStride apart, which makes the
+  // leading barrier unnecessary (a buffer is rewritten only two exchanges
+  // later, behind the intermediate exchange's barrier).
+  template<int NA, class Lay, bool PP>
   static __device__ __forceinline__ void exchange(double2 (&x)[NA][8], int tau,
                                                   int lsFrom, int lsTo,
                                                   double2 *buf, int bufStride,
-                                                  const Lay& lay, bool active) {
-    lay.sync();
+                                                  const Lay& lay, bool active,
+                                                  int& pp, int ppStride) {
+    if(PP && ppStride) {
+      buf += pp*ppStride;
+      pp ^= 1;
+    } else
+      lay.sync();
     if(active) {
 #pragma unroll
       for(int a=0; a < NA; ++a)
@@ -194,11 +202,15 @@ struct RegFFT {
   }
 
   // in: x[a][t]=W_a[tau+TPT*t]; out: x[a][e]=FFT at scrambled position 8*tau+e
-  template<int NA, class Lay, bool SM=false>
+  template<int NA, class Lay, bool SM=false, bool PP=false>
   static __device__ __forceinline__ void forward(double2 (&x)[NA][8], int tau,
                                                  const double2 *__restrict__ tw,
                                                  double2 *buf, int bufStride,
-                                                 const Lay& lay, bool active) {
+                                                 const Lay& lay, bool active,
+                                                 int *pp=NULL,
+                                                 int ppStride=0) {
+    int dummy=0;
+    int& ppr=PP ? *pp : dummy;
 #pragma unroll
     for(int i=0; i < NR8; ++i) {
       const int ls=LG-3*(i+1);
@@ -214,7 +226,8 @@ struct RegFFT {
       }
       const int lsNext=(i+1 < NR8) ? LG-3*(i+2) : 0;
       if(i+1 < NR8 || REM > 0)
-        exchange<NA>(x,tau,ls,lsNext,buf,bufStride,lay,active);
+        exchange<NA,Lay,PP>(x,tau,ls,lsNext,buf,bufStride,lay,active,ppr,
+                            ppStride);
     }
 #pragma unroll
     for(int a=0; a < NA; ++a) {
@@ -231,11 +244,15 @@ struct RegFFT {
   }
 
   // exact adjoint of forward(): in scrambled positions, out x[t]=w[tau+TPT*t]
-  template<int NA, class Lay, bool SM=false>
+  template<int NA, class Lay, bool SM=false, bool PP=false>
   static __device__ __forceinline__ void adjoint(double2 (&x)[NA][8], int tau,
                                                  const double2 *__restrict__ tw,
                                                  double2 *buf, int bufStride,
-                                                 const Lay& lay, bool active) {
+                                                 const Lay& lay, bool active,
+                                                 int *pp=NULL,
+                                                 int ppStride=0) {
+    int dummy=0;
+    int& ppr=PP ? *pp : dummy;
 #pragma unroll
     for(int a=0; a < NA; ++a) {
       if(REM == 2) {
@@ -253,7 +270,8 @@ struct RegFFT {
       const int ls=LG-3*(i+1);
       const int lsPrev=(i+1 < NR8) ? LG-3*(i+2) : 0;
       if(i+1 < NR8 || REM > 0)
-        exchange<NA>(x,tau,lsPrev,ls,buf,bufStride,lay,active);
+        exchange<NA,Lay,PP>(x,tau,lsPrev,ls,buf,bufStride,lay,active,ppr,
+                            ppStride);
       if(ls > 0) {
 #pragma unroll
         for(int u=1; u < 8; ++u) {
@@ -319,8 +337,6 @@ struct Word {typedef double2 type;};
 template<>
 struct Word<FFTWPP_KIND_REAL> {typedef double type;};
 
-__device__ __forceinline__ double2 toC(double2 v) {return v;}
-__device__ __forceinline__ double2 toC(double v) {return make_double2(v,0.0);}
 
 // ---------------------------------------------------------------------------
 // fused 1-D convolution over contiguous rows (COMPLEX kind, A=2, B=1)
@@ -673,7 +689,8 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
                                            double2 *buf, void *F,
                                            long long Fbase, int T, int col0,
                                            bool colsok, long long plane,
-                                           long long rs)
+                                           long long rs, int& pp,
+                                           int ppStride)
 {
   typedef RegFFT<LG> FFT;
   const int mlen=FFT::N;
@@ -713,8 +730,9 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
       }
     }
   }
-  FFT::template forward<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[which],
-                                           buf,0,lay,active);
+  FFT::template forward<1,LaneLayout,true,true>(x,active ? tau : 0,
+                                                tb.tw[which],buf,0,lay,active,
+                                                &pp,ppStride);
   if(active && colsok) {
     const long long row0=P.omBase ? sb.off_all/P.S : 0;
 #pragma unroll
@@ -754,7 +772,8 @@ __device__ __forceinline__ void forwardSubPaired(const PlanDev& P,
                                                  double2 *buf, void *F,
                                                  long long Fbase, int T,
                                                  int col0, long long plane,
-                                                 long long rs)
+                                                 long long rs, int& pp,
+                                                 int ppStride)
 {
   typedef RegFFT<LG> FFT;
   const int M=FFT::N;
@@ -783,8 +802,8 @@ __device__ __forceinline__ void forwardSubPaired(const PlanDev& P,
       x[0][t]=acc;
     }
   }
-  FFT::template forward<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[0],buf,0,
-                                           lay,active);
+  FFT::template forward<1,LaneLayout,true,true>(x,active ? tau : 0,tb.tw[0],
+                                                buf,0,lay,active,&pp,ppStride);
   // natural-order copy for the partner lookup
   __syncthreads();
   if(active) {
@@ -820,6 +839,7 @@ __device__ __forceinline__ void forwardSubPaired(const PlanDev& P,
       }
     }
   }
+  __syncthreads(); // partner reads done before the buffer is reused
 }
 
 template<int LG>
@@ -829,7 +849,8 @@ __device__ __forceinline__ void backwardSubPaired(const PlanDev& P,
                                                   double *acc, double2 *buf,
                                                   const void *F,
                                                   long long Fbase, int T,
-                                                  int col0)
+                                                  int col0, int& pp,
+                                                  int ppStride)
 {
   typedef RegFFT<LG> FFT;
   const int M=FFT::N;
@@ -860,8 +881,8 @@ __device__ __forceinline__ void backwardSubPaired(const PlanDev& P,
       x[0][e]=make_double2(ga.x-gb.y,ga.y+gb.x); // ga + i gb
     }
   }
-  FFT::template adjoint<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[0],buf,0,
-                                           lay,active);
+  FFT::template adjoint<1,LaneLayout,true,true>(x,active ? tau : 0,tb.tw[0],
+                                                buf,0,lay,active,&pp,ppStride);
   if(active) {
 #pragma unroll
     for(int t=0; t < 8; ++t) {
@@ -921,11 +942,13 @@ __global__ void __launch_bounds__(512)
 fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                   int layout, const void *f, void *F, long long nrows,
                   long long frs, long long Frs, int T, int ntc, size_t inbytes,
-                  int zlen, int mixed, long long ntiles, int pair)
+                  int zlen, int mixed, long long ntiles, int pair,
+                  int ppStride)
 {
   typedef typename Word<KIND>::type word;
   extern __shared__ __align__(16) double2 sm2[];
   const int M=1 << LG;
+  int pp=0;
   ManyTables tb;
   double2 *rest=loadTables<LG>(P,sbs,nsb,sm2,zlen,mixed != 0,tb);
   word *in=(word *) rest;
@@ -978,13 +1001,13 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
       if(sb.k0 != 0) ++slot;
       if(KIND == FFTWPP_KIND_REAL && !DIRECT && pair && (int) sb.mlen == M)
         forwardSubPaired<LG>(P,sb,tb,(const double *) src,buf,F,Fbase,T,col0,
-                             row,rs);
+                             row,rs,pp,ppStride);
       else if((int) sb.mlen == M)
         forwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,src,xin,buf,F,Fbase,T,
-                                   col0,colsok,row,rs);
+                                   col0,colsok,row,rs,pp,ppStride);
       else
         forwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,src,xin,buf,F,Fbase,T,
-                                    col0,colsok,row,rs);
+                                    col0,colsok,row,rs,pp,ppStride);
     }
     if(!DIRECT && inbytes) __syncthreads(); // tile reads done before restaging
   }
@@ -1032,7 +1055,8 @@ __device__ __forceinline__ void backwardSub(const PlanDev& P,
                                             const ManyTables& tb, int which,
                                             void *acc, double2 (&racc)[8],
                                             double2 *buf,
-                                            const double2 (&xin)[8], int T)
+                                            const double2 (&xin)[8], int T,
+                                            int& pp, int ppStride)
 {
   typedef RegFFT<LG> FFT;
   const int mlen=FFT::N;
@@ -1047,8 +1071,9 @@ __device__ __forceinline__ void backwardSub(const PlanDev& P,
   double2 x[1][8];
 #pragma unroll
   for(int t=0; t < 8; ++t) x[0][t]=xin[t];
-  FFT::template adjoint<1,LaneLayout,true>(x,active ? tau : 0,tb.tw[which],
-                                           buf,0,lay,active);
+  FFT::template adjoint<1,LaneLayout,true,true>(x,active ? tau : 0,
+                                                tb.tw[which],buf,0,lay,active,
+                                                &pp,ppStride);
   if(active) {
     if(DIRECT) {
 #pragma unroll
@@ -1089,11 +1114,12 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                    int layout, const void *F, void *f, int accum, double scale,
                    long long nrows, long long Frs, long long frs, int T,
                    int ntc, size_t accbytes, int zlen, int mixed,
-                   long long ntiles, int pair)
+                   long long ntiles, int pair, int ppStride)
 {
   typedef typename Word<KIND>::type word;
   extern __shared__ __align__(16) double2 sm2[];
   const int M=1 << LG;
+  int pp=0;
   ManyTables tb;
   double2 *rest=loadTables<LG>(P,sbs,nsb,sm2,zlen,mixed != 0,tb);
   word *acc=(word *) rest;
@@ -1165,17 +1191,21 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                                 row*Frs+(layout ? s1.off_all : s1.off_call),
                                 T,col0,colsok,xn);
         }
-        backwardSub<KIND,LG,true>(P,sb,myslot,tb,0,acc,racc,buf,xc,T);
+        backwardSub<KIND,LG,true>(P,sb,myslot,tb,0,acc,racc,buf,xc,T,pp,
+                                  ppStride);
 #pragma unroll
         for(int t=0; t < 8; ++t) xc[t]=xn[t];
       } else if(KIND == FFTWPP_KIND_REAL && pair && (int) sb.mlen == M) {
-        backwardSubPaired<LG>(P,sb,tb,(double *) acc,buf,F,Fbase,T,col0);
+        backwardSubPaired<LG>(P,sb,tb,(double *) acc,buf,F,Fbase,T,col0,pp,
+                              ppStride);
       } else if((int) sb.mlen == M) {
         loadSpectrum<KIND,LG>(P,sb,F,Fbase,T,col0,colsok,xc);
-        backwardSub<KIND,LG,false>(P,sb,myslot,tb,0,acc,racc,buf,xc,T);
+        backwardSub<KIND,LG,false>(P,sb,myslot,tb,0,acc,racc,buf,xc,T,pp,
+                                   ppStride);
       } else {
         loadSpectrum<KIND,LG-1>(P,sb,F,Fbase,T,col0,colsok,xc);
-        backwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,acc,racc,buf,xc,T);
+        backwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,acc,racc,buf,xc,T,pp,
+                                     ppStride);
       }
     }
     if(DIRECT) {
@@ -1255,6 +1285,18 @@ int tileLanes()
   return T;
 }
 
+// measured: no gain from ping-pong exchange buffers (the barriers are not
+// the limiter); kept as an experiment switch
+bool pingpongEnabled()
+{
+  static int on=-1;
+  if(on < 0) {
+    const char *s=getenv("FFTWPP_PINGPONG");
+    on=(s && *s && *s != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 int realLanes()
 {
   static int T=-1;
@@ -1311,7 +1353,7 @@ bool fastDisabled()
   }
 
 struct ManyGeom {
-  int T, nthreads, ntc, zlen, mixed, pair;
+  int T, nthreads, ntc, zlen, mixed, pair, ppStride;
   size_t tilebytes, smem;
   uint64_t ntiles, grid;
   bool direct;
@@ -1351,8 +1393,15 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g,
     // exchange buffer: M points per lane; paired r2c blocks use T/2 complex
     // lanes plus one padding row per 8 for the natural-order partner lookup
     size_t bufwords=g.pair ? (size_t) (M+M/8)*(T/2) : (size_t) M*T;
+    // ping-pong exchange buffers (one barrier per exchange) when two CTAs
+    // still fit per SM, else a single buffer with two barriers
+    size_t fixed=(size_t) twn*sizeof(double2)+g.tilebytes+
+      (size_t) std::min<size_t>(nz*span*sizeof(double2),48*1024);
+    bool pingpong=pingpongEnabled() &&
+      fixed+2*bufwords*sizeof(double2) <= 112*1024;
+    g.ppStride=pingpong ? (int) bufwords : 0;
     size_t base=(size_t) twn*sizeof(double2)+g.tilebytes+
-      bufwords*sizeof(double2);
+      (pingpong ? 2 : 1)*bufwords*sizeof(double2);
     size_t zbytes=(size_t) nz*span*sizeof(double2);
     g.zlen=span;
     if(zbytes > 48*1024 || base+zbytes > SMEM_MAX) {g.zlen=0; zbytes=0;}
@@ -1399,7 +1448,7 @@ int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
   fast_forward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
     (dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,            \
      (long long) frs,(long long) Frs,g.T,g.ntc,g.tilebytes,g.zlen,g.mixed,   \
-     (long long) g.ntiles,g.pair);
+     (long long) g.ntiles,g.pair,g.ppStride);
 #define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
   LG_CASES(CALL)
 #undef CALL
@@ -1433,7 +1482,7 @@ int launchBackwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb,
   fast_backward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
     (dev,pl->dsub+sb0,(int) nsb,layout,F,f,accumulate,scale,             \
      (long long) nrows,(long long) Frs,(long long) frs,g.T,g.ntc,            \
-     g.tilebytes,g.zlen,g.mixed,(long long) g.ntiles,g.pair);
+     g.tilebytes,g.zlen,g.mixed,(long long) g.ntiles,g.pair,g.ppStride);
 #define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
   LG_CASES(CALL)
 #undef CALL
