@@ -213,3 +213,79 @@ def test_cfg3_shape_hermitian_3d():
     """BASELINE configs[2] geometry (centred x,y + Hermitian z, M=3L/2) at 64^3."""
     check(fp.FAMILY_HERMITIAN, (64, 64, 64), None, seed=64)
     check(fp.FAMILY_HERMITIAN, (128, 32, 256), None, seed=65)
+
+
+def _strided(a, shape_alloc):
+    """Embed array a in a larger zero array (the reference's -Sx/-Sy stride
+    variants, tests/tests.py:393-459) and return (buffer, view)."""
+    buf = np.zeros(shape_alloc, dtype=a.dtype)
+    buf[tuple(slice(0, n) for n in a.shape)] = a
+    return buf
+
+
+@pytest.mark.parametrize("fam", [fp.FAMILY_COMPLEX, fp.FAMILY_REAL])
+@pytest.mark.parametrize("L", [(8, 6), (16, 16), (33, 12), (64, 32)])
+def test_conv2d_with_x_stride(fam, L):
+    Lx, Ly = L
+    Sx = Ly + 3 if fam == fp.FAMILY_COMPLEX else Ly + 2
+    rng = np.random.default_rng(Lx * Ly)
+    if fam == fp.FAMILY_COMPLEX:
+        f, g = crand(rng, Lx, Ly), crand(rng, Lx, Ly)
+        want = O.conv_complex(f, g)
+    else:
+        f, g = rng.uniform(-1, 1, L), rng.uniform(-1, 1, L)
+        want = O.conv_real(f, g)
+    conv = fp.HybridConv([Lx, Ly], [2 * Lx, 2 * Ly], family=fam, Sx=Sx)
+    a = [_strided(f, (Lx, Sx)), _strided(g, (Lx, Sx))]
+    conv.convolve(a)
+    assert O.rel_l2(a[0][:, :Ly], want) < 1e-12
+
+
+@pytest.mark.parametrize("fam", [fp.FAMILY_COMPLEX, fp.FAMILY_REAL])
+@pytest.mark.parametrize("L,gaps", [((6, 5, 4), (0, 3)), ((6, 5, 4), (2, 0)), ((6, 5, 4), (2, 3)),
+                                    ((16, 16, 16), (1, 2)), ((32, 8, 64), (4, 4))])
+def test_conv3d_with_strides(fam, L, gaps):
+    """Sy > Lz exercises the non-contiguous x pass of Convolution3
+    (reference convolve.h:1727-1735), Sx > Ly*Sy the x stride."""
+    Lx, Ly, Lz = L
+    Sy = Lz + gaps[0]
+    Sx = Ly * Sy + gaps[1]
+    if fam == fp.FAMILY_REAL:
+        # doubles: keep strides even so Complex-typed offsets stay aligned
+        Sy += Sy % 2
+        Sx = Ly * Sy + 2 * (gaps[1] // 2)
+    rng = np.random.default_rng(Lx + Ly + Lz)
+    if fam == fp.FAMILY_COMPLEX:
+        f, g = crand(rng, *L), crand(rng, *L)
+        want = O.conv_complex(f, g)
+    else:
+        f, g = rng.uniform(-1, 1, L), rng.uniform(-1, 1, L)
+        want = O.conv_real(f, g)
+    conv = fp.HybridConv(list(L), [2 * l for l in L], family=fam, Sx=Sx, Sy=Sy)
+
+    def embed(a):
+        buf = np.zeros(Lx * Sx, dtype=a.dtype)
+        for i in range(Lx):
+            for j in range(Ly):
+                buf[i * Sx + j * Sy: i * Sx + j * Sy + Lz] = a[i, j]
+        return buf
+
+    a = [embed(f), embed(g)]
+    conv.convolve(a)
+    got = np.array([[a[0][i * Sx + j * Sy: i * Sx + j * Sy + Lz] for j in range(Ly)]
+                    for i in range(Lx)])
+    assert O.rel_l2(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("A,B", [(1, 1), (3, 3), (3, 2)])
+def test_multnone_general_A_B(A, B):
+    """multNone with general A >= B: forward/backward identity times N
+    (Application(A,B,multNone), reference convolve.h:84-121)."""
+    L = 24
+    rng = np.random.default_rng(A * 10 + B)
+    arrays = [crand(rng, L) for _ in range(max(A, B))]
+    keep = [a.copy() for a in arrays]
+    conv = fp.HybridConv([L], [2 * L], A=A, B=B, mult=fp.MULT_NONE)
+    conv.convolve(arrays)
+    for b in range(B):
+        assert O.rel_l2(arrays[b], keep[b]) < 1e-12
