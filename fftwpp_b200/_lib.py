@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _here = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_here, "lib_fftwpp.so")
+# FFTWPP_LIB selects another in-tree build (kernel A/B experiments)
+lib_path = os.path.join(_here, os.environ.get("FFTWPP_LIB", "lib_fftwpp.so"))
 
 
 class LibraryMissing(ImportError):

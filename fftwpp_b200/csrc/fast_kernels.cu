@@ -28,6 +28,10 @@
 
 #include <mutex>
 
+#ifndef FFTWPP_TWMODE
+#define FFTWPP_TWMODE 1
+#endif
+
 namespace fftwpp_gpu {
 
 struct FastInfo {
@@ -163,6 +167,35 @@ struct RegFFT {
     return SM ? *p : __ldg(p);
   }
 
+  // The seven twiddles w^1..w^7 of pass i.  Shared-memory bandwidth, not
+  // FP64 issue, limits these kernels, so only w, w^2 and w^4 are read and the
+  // other four are products of those (TWM 1, the strided passes), or w alone
+  // is read (TWM 2, the fused convolutions); TWM 0 reads all seven.
+  template<bool SM, int TWM>
+  static __device__ __forceinline__ void twiddles(const double2 *tw, int i,
+                                                  int tau, double2 (&w)[8]) {
+    if(TWM == 0) {
+#pragma unroll
+      for(int u=1; u < 8; ++u) w[u]=twid<SM>(tw,i,u,tau);
+    } else if(TWM == 1) {
+      w[1]=twid<SM>(tw,i,1,tau);
+      w[2]=twid<SM>(tw,i,2,tau);
+      w[4]=twid<SM>(tw,i,4,tau);
+      w[3]=fmul(w[1],w[2]);
+      w[5]=fmul(w[1],w[4]);
+      w[6]=fmul(w[2],w[4]);
+      w[7]=fmul(w[3],w[4]);
+    } else {
+      w[1]=twid<SM>(tw,i,1,tau);
+      w[2]=fmul(w[1],w[1]);
+      w[3]=fmul(w[1],w[2]);
+      w[4]=fmul(w[2],w[2]);
+      w[5]=fmul(w[1],w[4]);
+      w[6]=fmul(w[3],w[3]);
+      w[7]=fmul(w[3],w[4]);
+    }
+  }
+
   // position of register t of thread tau in a pass whose legs are 2^ls apart
   static __device__ __forceinline__ int pos(int tau, int t, int ls) {
     return ((tau >> ls) << (ls+3))+(tau & ((1 << ls)-1))+(t << ls);
@@ -202,7 +235,8 @@ struct RegFFT {
   }
 
   // in: x[a][t]=W_a[tau+TPT*t]; out: x[a][e]=FFT at scrambled position 8*tau+e
-  template<int NA, class Lay, bool SM=false, bool PP=false>
+  template<int NA, class Lay, bool SM=false, bool PP=false,
+           int TWM=FFTWPP_TWMODE>
   static __device__ __forceinline__ void forward(double2 (&x)[NA][8], int tau,
                                                  const double2 *__restrict__ tw,
                                                  double2 *buf, int bufStride,
@@ -217,12 +251,12 @@ struct RegFFT {
 #pragma unroll
       for(int a=0; a < NA; ++a) bfly8<1>(x[a]);
       if(ls > 0) {
+        double2 w[8];
+        twiddles<SM,TWM>(tw,i,tau,w);
 #pragma unroll
-        for(int u=1; u < 8; ++u) {
-          const double2 w=twid<SM>(tw,i,u,tau);
+        for(int u=1; u < 8; ++u)
 #pragma unroll
-          for(int a=0; a < NA; ++a) x[a][u]=fmul(x[a][u],w);
-        }
+          for(int a=0; a < NA; ++a) x[a][u]=fmul(x[a][u],w[u]);
       }
       const int lsNext=(i+1 < NR8) ? LG-3*(i+2) : 0;
       if(i+1 < NR8 || REM > 0)
@@ -244,7 +278,8 @@ struct RegFFT {
   }
 
   // exact adjoint of forward(): in scrambled positions, out x[t]=w[tau+TPT*t]
-  template<int NA, class Lay, bool SM=false, bool PP=false>
+  template<int NA, class Lay, bool SM=false, bool PP=false,
+           int TWM=FFTWPP_TWMODE>
   static __device__ __forceinline__ void adjoint(double2 (&x)[NA][8], int tau,
                                                  const double2 *__restrict__ tw,
                                                  double2 *buf, int bufStride,
@@ -273,12 +308,12 @@ struct RegFFT {
         exchange<NA,Lay,PP>(x,tau,lsPrev,ls,buf,bufStride,lay,active,ppr,
                             ppStride);
       if(ls > 0) {
+        double2 w[8];
+        twiddles<SM,TWM>(tw,i,tau,w);
 #pragma unroll
-        for(int u=1; u < 8; ++u) {
-          const double2 w=twid<SM>(tw,i,u,tau);
+        for(int u=1; u < 8; ++u)
 #pragma unroll
-          for(int a=0; a < NA; ++a) x[a][u]=fmulc(x[a][u],w);
-        }
+          for(int a=0; a < NA; ++a) x[a][u]=fmulc(x[a][u],w[u]);
       }
 #pragma unroll
       for(int a=0; a < NA; ++a) bfly8<-1>(x[a]);
@@ -453,8 +488,8 @@ fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
           }
         }
       }
-      FFT::template forward<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
-      FFT::template forward<1,RowLayout,true>(y,tau,tws,bufs,0,lay,true);
+      FFT::template forward<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
+      FFT::template forward<1,RowLayout,true,false,2>(y,tau,tws,bufs,0,lay,true);
       if(mult == FFTWPP_MULT_BINARY) {
 #pragma unroll
         for(int t=0; t < 8; ++t) x[0][t]=fmul(x[0][t],y[0][t]);
@@ -462,7 +497,7 @@ fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
 #pragma unroll
         for(int t=0; t < 8; ++t) x[0][t]=fmulc(x[0][t],y[0][t]);
       }
-      FFT::template adjoint<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
+      FFT::template adjoint<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
       if(isb > 0) {
 #pragma unroll
         for(int k=0; k < NTERM; ++k)
@@ -496,6 +531,165 @@ fast_conv_rows(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
     }
     // the next group's first exchange starts with a barrier, which also
     // orders this group's last reads of the exchange buffers
+  }
+}
+
+// Software-pipelined variant for L <= m (one input term per W[s], the shape
+// of every p=1 configuration): the kernel is bound by the latency of its
+// global loads at 16 warps/SM, so each work item (row, sub-block) issues the
+// loads of the NEXT item's second input right after the multiplier, where
+// those registers fall free, and the loads of its own first input just before
+// the FFT of the second -- both land while an FFT runs.  The running sum over
+// sub-blocks rests in the idle half of the row's shared-memory buffer between
+// items, so no accumulator registers are live across the FFTs.
+template<int LG>
+__global__ void __launch_bounds__((1 << LG)/8 > 256 ? (1 << LG)/8 : 256, (1 << LG)/8 > 256 ? 1 : 2)
+fast_conv_rows_pipe(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
+                    double2 *f0, const double2 *f1, int mult, double scale,
+                    long long nrows, long long rs, int tabid, int zlen,
+                    long long ngroups)
+{
+  typedef RegFFT<LG> FFT;
+  const int M=FFT::N;
+  const int TPT=FFT::TPT;
+  const int NT=TPT > 256 ? TPT : 256;
+  const int ROWS=NT/TPT;
+  const int TWN=FFT::twCount();
+  const int BUF=M+M/8;
+  extern __shared__ __align__(16) double2 sm[];
+  double2 *tws=sm;
+  double2 *zs=sm+TWN;
+  int nz=0;
+  for(int isb=0; isb < nsb; ++isb) nz += sbs[isb].k0 != 0;
+  double2 *bufs=zs+(zlen ? (size_t) nz*zlen : 0);
+  const int rowInCta=threadIdx.x/TPT;
+  const int tau=threadIdx.x % TPT;
+  const int L=P.jmax;
+
+  {
+    const double2 *tw=P.tab[tabid].tw8;
+    for(int i=threadIdx.x; i < TWN; i += NT) tws[i]=__ldg(tw+i);
+    if(zlen) {
+      int slot=0;
+      for(int isb=0; isb < nsb; ++isb) {
+        const long long k0=sbs[isb].k0;
+        if(k0 == 0) continue;
+        for(int j=threadIdx.x; j < zlen; j += NT)
+          zs[(size_t) slot*zlen+j]=zeta(P,modN(P,k0,j));
+        ++slot;
+      }
+    }
+  }
+  __syncthreads();
+
+  RowLayout lay;
+  lay.base=rowInCta*2*BUF;
+  lay.barid=TPT > 32 ? 1+rowInCta : 0;
+  lay.nthreads=TPT;
+  double2 *park=bufs+lay.base+BUF+tau;
+
+  long long grp=blockIdx.x;
+  if(grp >= ngroups) return;
+  double2 x[1][8], y[1][8];
+  {
+    long long row=grp*ROWS+rowInCta;
+    if(row >= nrows) row=nrows-1;
+    const double2 *g1=f1+row*rs;
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+      const int j=tau+TPT*t;
+      y[0][t]=j < L ? g1[j] : make_double2(0.0,0.0);
+    }
+  }
+
+  for(; grp < ngroups; grp += gridDim.x) {
+    long long row=grp*ROWS+rowInCta;
+    const bool live=row < nrows;
+    if(!live) row=nrows-1;
+    double2 *g0=f0+row*rs;
+    const double2 *g1=f1+row*rs;
+    const long long ngrp=grp+gridDim.x;
+    const bool more=ngrp < ngroups;
+    long long nrow=ngrp*ROWS+rowInCta;
+    if(nrow >= nrows) nrow=nrows-1;
+    const double2 *n1=f1+nrow*rs;
+    { // pull the group after next into L2 ahead of its register loads
+      long long prow=(ngrp+gridDim.x)*ROWS+rowInCta;
+      if(prow < nrows) {
+        const char *p0=(const char *) (f0+prow*rs);
+        const char *p1=(const char *) (f1+prow*rs);
+        for(int off=tau*128; off < L*16; off += TPT*128) {
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
+        }
+      }
+      if(grp == blockIdx.x && more) { // first iteration: the next group too
+        const char *p0=(const char *) (f0+nrow*rs);
+        for(int off=tau*128; off < L*16; off += TPT*128)
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
+      }
+    }
+
+    int slot=0;
+    for(int isb=0; isb < nsb; ++isb) {
+      const long long k0=sbs[isb].k0;
+      const double2 *zrow=zs+(size_t) slot*zlen;
+      if(k0 != 0) ++slot;
+      // this item's first input: in flight during the FFT of the second
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        const int j=tau+TPT*t;
+        x[0][t]=j < L ? g0[j] : make_double2(0.0,0.0);
+      }
+      if(k0 != 0) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          const int j=tau+TPT*t;
+          if(j < L)
+            y[0][t]=fmul(y[0][t],zlen ? zrow[j] : zeta(P,modN(P,k0,j)));
+        }
+      }
+      FFT::template forward<1,RowLayout,true,false,2>(y,tau,tws,bufs,0,lay,true);
+      if(k0 != 0) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          const int j=tau+TPT*t;
+          if(j < L)
+            x[0][t]=fmul(x[0][t],zlen ? zrow[j] : zeta(P,modN(P,k0,j)));
+        }
+      }
+      FFT::template forward<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
+      if(mult == FFTWPP_MULT_BINARY) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) x[0][t]=fmul(x[0][t],y[0][t]);
+      } else {
+#pragma unroll
+        for(int t=0; t < 8; ++t) x[0][t]=fmulc(x[0][t],y[0][t]);
+      }
+      // the next item's second input: in flight during the inverse FFT
+      const bool lastsb=isb+1 == nsb;
+      if(!lastsb || more) {
+        const double2 *h1=lastsb ? n1 : g1;
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          const int j=tau+TPT*t;
+          y[0][t]=j < L ? h1[j] : make_double2(0.0,0.0);
+        }
+      }
+      FFT::template adjoint<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        const int j=tau+TPT*t;
+        if(j < L) {
+          double2 v=x[0][t];
+          if(k0 != 0)
+            v=fmulc(v,zlen ? zrow[j] : zeta(P,modN(P,k0,j)));
+          if(isb > 0) v=v+park[t*TPT];
+          if(!lastsb) park[t*TPT]=v;
+          else if(live) g0[j]=make_double2(v.x*scale,v.y*scale);
+        }
+      }
+    }
   }
 }
 
@@ -604,11 +798,11 @@ fast_conv_rows_herm(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
         // Z = W_0 + i W_1
         x[0][t]=make_double2(wa.x-wb.y,wa.y+wb.x);
       }
-      FFT::template forward<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
+      FFT::template forward<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
 #pragma unroll
       for(int t=0; t < 8; ++t)
         x[0][t]=make_double2(x[0][t].x*x[0][t].y,0.0); // realMultBinary
-      FFT::template adjoint<1,RowLayout,true>(x,tau,tws,bufs,0,lay,true);
+      FFT::template adjoint<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
       if(isb > 0) {
 #pragma unroll
         for(int t=0; t < 8; ++t) acc[t]=park[t*TPT];
@@ -680,7 +874,13 @@ __device__ __forceinline__ double2 zetaAt(const PlanDev& P,
   return zeta(P,modN(P,k0,j));
 }
 
-template<int KIND, int LG, bool DIRECT>
+struct NoPrefetch {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// `pre` runs after the thread's inputs have been consumed and before the FFT:
+// the DIRECT kernels use it to put the next tile's loads in flight.
+template<int KIND, int LG, bool DIRECT, class Pre>
 __device__ __forceinline__ void forwardSub(const PlanDev& P,
                                            const SubBlockDev& sb, int slot,
                                            const ManyTables& tb, int which,
@@ -690,7 +890,7 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
                                            long long Fbase, int T, int col0,
                                            bool colsok, long long plane,
                                            long long rs, int& pp,
-                                           int ppStride)
+                                           int ppStride, const Pre& pre)
 {
   typedef RegFFT<LG> FFT;
   const int mlen=FFT::N;
@@ -730,6 +930,7 @@ __device__ __forceinline__ void forwardSub(const PlanDev& P,
       }
     }
   }
+  pre();
   FFT::template forward<1,LaneLayout,true,true>(x,active ? tau : 0,
                                                 tb.tw[which],buf,0,lay,active,
                                                 &pp,ppStride);
@@ -957,6 +1158,22 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   const int tau=threadIdx.x/T;
   __syncthreads();
 
+  // DIRECT: the thread's 8 input points, reused by every sub-block.  (Loading
+  // the next tile's points during the last sub-block's FFT was measured
+  // slower: the persistent CTAs already overlap through 2 CTAs/SM.)
+  double2 xin[8];
+  auto loadDirect=[&](long long t_) {
+    const int c0=(int) (t_ % ntc)*T;
+    const double2 *gg=(const double2 *) f+(t_/ntc)*frs+c0+lane;
+    const bool ok=c0+lane < P.C;
+    const int TPT=M/8;
+#pragma unroll
+    for(int t=0; t < 8; ++t) {
+      int j=tau+TPT*t;
+      xin[t]=(ok && j < P.jmax) ? gg[P.S*j] : make_double2(0.0,0.0);
+    }
+  };
+
   for(long long tile=blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row=tile/ntc;
     const int col0=(int) (tile % ntc)*T;
@@ -971,15 +1188,8 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
           asm volatile("prefetch.global.L2 [%0];" :: "l"(ng+P.S*j));
       }
     }
-    double2 xin[8];
     if(DIRECT) {
-      const int TPT=M/8;
-#pragma unroll
-      for(int t=0; t < 8; ++t) {
-        int j=tau+TPT*t;
-        xin[t]=(colsok && j < P.jmax) ?
-          ((const double2 *) g)[P.S*j+lane] : make_double2(0.0,0.0);
-      }
+      loadDirect(tile);
     } else if(inbytes) {
       // stage the input tile: T contiguous words per logical row
       const int total=P.Lin*T;
@@ -1004,10 +1214,12 @@ fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                              row,rs,pp,ppStride);
       else if((int) sb.mlen == M)
         forwardSub<KIND,LG,DIRECT>(P,sb,myslot,tb,0,src,xin,buf,F,Fbase,T,
-                                   col0,colsok,row,rs,pp,ppStride);
+                                   col0,colsok,row,rs,pp,ppStride,
+                                   NoPrefetch());
       else
         forwardSub<KIND,LG-1,false>(P,sb,myslot,tb,1,src,xin,buf,F,Fbase,T,
-                                    col0,colsok,row,rs,pp,ppStride);
+                                    col0,colsok,row,rs,pp,ppStride,
+                                    NoPrefetch());
     }
     if(!DIRECT && inbytes) __syncthreads(); // tile reads done before restaging
   }
@@ -1128,6 +1340,7 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   const int tau=threadIdx.x/T;
   __syncthreads();
 
+  double2 xc[8];
   for(long long tile=blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row=tile/ntc;
     const int col0=(int) (tile % ntc)*T;
@@ -1170,7 +1383,6 @@ fast_backward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
       __syncthreads();
     }
     int slot=0;
-    double2 xc[8];
     if(DIRECT) {
       // software pipeline: the next sub-block's loads are in flight while
       // the current one is transformed
@@ -1326,6 +1538,18 @@ bool pairDisabled()
     off=(s && *s && *s != '0') ? 1 : 0;
   }
   return off == 1;
+}
+
+// software-pipelined fused convolution (FFTWPP_CONV_PIPE=0 selects the
+// plain kernel for A/B timing)
+bool convPipeEnabled()
+{
+  static int on=-1;
+  if(on < 0) {
+    const char *s=getenv("FFTWPP_CONV_PIPE");
+    on=(s && *s == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 bool fastDisabled()
@@ -1517,6 +1741,20 @@ int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
   uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) 148*2*4);
   int tabid=0;
   int rc=0;
+  if(NTERM == 1 && convPipeEnabled()) {
+#define CALL(LGV)                                                            \
+    rc=allowSmem(fast_conv_rows_pipe<LGV>);                                  \
+    if(rc) return rc;                                                        \
+    prof_begin(4*pl->tag+2,st);                                              \
+    fast_conv_rows_pipe<LGV><<<(unsigned) grid,NT,smem,st>>>                 \
+      (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],              \
+       (const double2 *) f[1],mult,scale,(long long) nrows,(long long) rs,   \
+       tabid,zlen,(long long) ngroups);
+    LG_CASES(CALL)
+#undef CALL
+    rc=check_launch("fast_conv_rows_pipe",st);
+    return rc ? rc : 1;
+  }
 #define CALL(LGV)                                                            \
   rc=allowSmem(fast_conv_rows<LGV,NTERM>);                                   \
   if(rc) return rc;                                                          \
