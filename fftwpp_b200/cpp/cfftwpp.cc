@@ -373,24 +373,35 @@ void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk)
 
 namespace {
 struct MpiConv {
+  int dim;
   Application *app[3];
   fftBase *fft[3];
-  Convolution3MPI *conv;
+  Convolution2MPI *conv2;
+  Convolution3MPI *conv3;
+  MpiConv() : dim(0), conv2(NULL), conv3(NULL) {
+    for(int d=0; d < 3; ++d) {app[d]=NULL; fft[d]=NULL;}
+  }
   ~MpiConv() {
-    delete conv;
+    delete conv2;
+    delete conv3;
     for(int d=2; d >= 0; --d) {delete fft[d]; delete app[d];}
   }
+  SlabTranspose *slab() {
+    return conv3 ? (SlabTranspose *) conv3 : (SlabTranspose *) conv2;
+  }
 };
-}
 
-void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
-                             const size_t *m, const size_t *D, const long *I,
-                             size_t A, size_t B, int mult, int rank, int size,
-                             void *comm)
+// dim 2: arrays Lx x y (y split); dim 3: Lx x y x Lz.  family as in
+// fftwpp_conv_create: 0 complex, 1 centred Hermitian (last dimension holds
+// the ceil(L/2) non-negative modes), 2 real.
+MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
+                     const size_t *m, const size_t *D, const long *I,
+                     size_t A, size_t B, int mult, int rank, int size,
+                     void *comm)
 {
-  if(family != 0 && family != 2) {
-    std::cerr << "distributed convolutions: family must be 0 (complex) or 2 "
-              << "(real)" << std::endl;
+  if(family < 0 || family > 2 || (dim == 2 && family == 2)) {
+    std::cerr << "distributed convolutions: unsupported dim/family "
+              << dim << "/" << family << std::endl;
     exit(-1);
   }
   size_t zero[3]={0,0,0};
@@ -399,38 +410,83 @@ void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
   if(!D) D=zero;
   if(!I) I=minus;
   MpiConv *c=new MpiConv;
+  c->dim=dim;
   utils::MPIgroup group(rank,size,comm);
+  int kinds[3];
+  size_t len[3];
+  for(int d=0; d < dim; ++d) {
+    if(family == 0) kinds[d]=0;
+    else if(family == 1) kinds[d]=(d == dim-1) ? 2 : 1;
+    else kinds[d]=(d == 0) ? 3 : 0;
+    len[d]=(family == 1 && d == dim-1) ? ceilquotient(L[d],2) : L[d];
+  }
+  // the split dimension is y: in 2-D Hermitian runs that is the half-length
+  // dimension, so the slices are taken over its stored modes
   size_t y0;
-  size_t y=utils::localdimension(L[1],rank,size,&y0);
-  for(int d=0; d < 3; ++d) {
-    multiplier *mu=(d == 2) ? pickMult(mult) : multNone;
+  size_t y=utils::localdimension(len[1],rank,size,&y0);
+  if(y == 0) {
+    std::cerr << "rank " << rank << " has an empty y slab (more ranks than "
+              << "ceil-split rows); reduce the number of ranks" << std::endl;
+    exit(-1);
+  }
+  if(dim == 2 && family == 1) {
+    std::cerr << "distributed 2-D Hermitian convolutions are not supported "
+              << "(the Hermitian dimension cannot be the split one)"
+              << std::endl;
+    exit(-1);
+  }
+  for(int d=0; d < dim; ++d) {
+    multiplier *mu=(d == dim-1) ? pickMult(mult) : multNone;
     long Id=m[d] > 0 ? I[d] : -1;
     if(d == 0)
       c->app[d]=new Application(A,B,mu,fftw::maxthreads,false,m[d],D[d],Id);
     else
       c->app[d]=new Application(A,B,mu,*c->app[d-1],m[d],D[d],Id);
   }
-  size_t Cx=std::max<size_t>(y,1)*L[2];
-  c->fft[0]=makePad(family == 2 ? 3 : 0,L[0],M[0],*c->app[0],Cx,Cx,m[0],D[0],
-                    I[0]);
-  c->fft[1]=makePad(0,L[1],M[1],*c->app[1],L[2],L[2],m[1],D[1],I[1]);
-  c->fft[2]=makePad(0,L[2],M[2],*c->app[2],1,0,m[2],D[2],I[2]);
-  if(y == 0) {
-    std::cerr << "rank " << rank << " has an empty y slab (more ranks than "
-              << "ceil-split rows); reduce the number of ranks" << std::endl;
-    exit(-1);
+  if(dim == 2) {
+    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],y,y,m[0],D[0],I[0]);
+    c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],1,0,m[1],D[1],I[1]);
+    c->conv2=new Convolution2MPI(c->fft[0],c->fft[1],group);
+  } else {
+    size_t Cx=y*len[2];
+    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],Cx,Cx,m[0],D[0],I[0]);
+    c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],len[2],len[2],m[1],D[1],
+                      I[1]);
+    c->fft[2]=makePad(kinds[2],L[2],M[2],*c->app[2],1,0,m[2],D[2],I[2]);
+    c->conv3=new Convolution3MPI(c->fft[0],c->fft[1],c->fft[2],group);
   }
-  c->conv=new Convolution3MPI(c->fft[0],c->fft[1],c->fft[2],group);
   return c;
+}
+}
+
+void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
+                             const size_t *m, const size_t *D, const long *I,
+                             size_t A, size_t B, int mult, int rank, int size,
+                             void *comm)
+{
+  return makeMpiConv(3,family,L,M,m,D,I,A,B,mult,rank,size,comm);
+}
+
+void *fftwpp_mpiconv2_create(int family, const size_t *L, const size_t *M,
+                             const size_t *m, const size_t *D, const long *I,
+                             size_t A, size_t B, int mult, int rank, int size,
+                             void *comm)
+{
+  return makeMpiConv(2,family,L,M,m,D,I,A,B,mult,rank,size,comm);
 }
 
 void fftwpp_mpiconv3_destroy(void *conv) {delete (MpiConv *) conv;}
+void fftwpp_mpiconv2_destroy(void *conv) {delete (MpiConv *) conv;}
 
 void fftwpp_mpiconv3_split(void *conv, size_t *out)
 {
-  utils::split3& d=((MpiConv *) conv)->conv->d;
+  utils::split3& d=((MpiConv *) conv)->slab()->d;
   out[0]=d.X; out[1]=d.Y; out[2]=d.Z; out[3]=d.x; out[4]=d.y; out[5]=d.z;
   out[6]=d.x0; out[7]=d.y0; out[8]=d.z0;
+}
+void fftwpp_mpiconv2_split(void *conv, size_t *out)
+{
+  fftwpp_mpiconv3_split(conv,out);
 }
 
 void fftwpp_mpiconv3_params(void *conv, int d, size_t *out)
@@ -439,12 +495,25 @@ void fftwpp_mpiconv3_params(void *conv, int d, size_t *out)
   out[0]=f->m; out[1]=f->p; out[2]=f->q; out[3]=f->n; out[4]=f->D;
   out[5]=f->inplace; out[6]=f->C; out[7]=f->S;
 }
+void fftwpp_mpiconv2_params(void *conv, int d, size_t *out)
+{
+  fftwpp_mpiconv3_params(conv,d,out);
+}
 
 void fftwpp_mpiconv3_convolve(void *conv, double **f, int normalized)
 {
-  Convolution3MPI *c=((MpiConv *) conv)->conv;
-  if(normalized) c->convolve((Complex **) f);
-  else c->convolveRaw((Complex **) f);
+  MpiConv *c=(MpiConv *) conv;
+  if(c->conv3) {
+    if(normalized) c->conv3->convolve((Complex **) f);
+    else c->conv3->convolveRaw((Complex **) f);
+  } else {
+    if(normalized) c->conv2->convolve((Complex **) f);
+    else c->conv2->convolveRaw((Complex **) f);
+  }
+}
+void fftwpp_mpiconv2_convolve(void *conv, double **f, int normalized)
+{
+  fftwpp_mpiconv3_convolve(conv,f,normalized);
 }
 
 void fftwpp_mpiconv3_exchange_table(void *conv, int direction,
@@ -453,15 +522,24 @@ void fftwpp_mpiconv3_exchange_table(void *conv, int direction,
                                     unsigned long long *rcount,
                                     unsigned long long *rdispl)
 {
-  ((MpiConv *) conv)->conv->exchangeTable(direction,(uint64_t *) scount,
-                                          (uint64_t *) sdispl,
-                                          (uint64_t *) rcount,
-                                          (uint64_t *) rdispl);
+  ((MpiConv *) conv)->slab()->exchangeTable(direction,(uint64_t *) scount,
+                                            (uint64_t *) sdispl,
+                                            (uint64_t *) rcount,
+                                            (uint64_t *) rdispl);
+}
+void fftwpp_mpiconv2_exchange_table(void *conv, int direction,
+                                    unsigned long long *scount,
+                                    unsigned long long *sdispl,
+                                    unsigned long long *rcount,
+                                    unsigned long long *rdispl)
+{
+  fftwpp_mpiconv3_exchange_table(conv,direction,scount,sdispl,rcount,rdispl);
 }
 
 void fftwpp_mpiconv3_set_plane_chunk(void *conv, size_t chunk)
 {
-  ((MpiConv *) conv)->conv->convolveyz[0]->planeChunk=chunk;
+  MpiConv *c=(MpiConv *) conv;
+  if(c->conv3) c->conv3->convolveyz[0]->planeChunk=chunk;
 }
 
 void fftwpp_set_stream(void *stream) {gpu::setStream(stream);}

@@ -9,9 +9,60 @@ using namespace utils;
 
 namespace fftwpp {
 
+SlabTranspose::SlabTranspose(const MPIgroup& group) : group(group)
+{
+  commStream=NULL;
+  nchunks=1;
+  const char *e=getenv("FFTWPP_MPI_CHUNKS");
+  if(e && *e) nchunks=std::max<size_t>(1,strtoull(e,NULL,10));
+}
+
+SlabTranspose::~SlabTranspose()
+{
+  for(size_t i=0; i < events.size(); ++i) fftwpp_gpu_event_destroy(events[i]);
+  if(commStream) fftwpp_gpu_stream_destroy(commStream);
+}
+
+Convolution2MPI::Convolution2MPI(fftBase *fftx, fftBase *ffty,
+                                 const MPIgroup& group) :
+  Convolution2(fftx,ffty), SlabTranspose(group)
+{
+  if(fftx->S != fftx->C) {
+    std::cerr << "Convolution2MPI: the local x pass must be contiguous (S == C)"
+              << std::endl;
+    exit(-1);
+  }
+  d=split3(fftx->allRows(),ffty->L,1,group);
+  if(fftx->C != d.y) {
+    std::cerr << "Convolution2MPI: fftx->C=" << fftx->C
+              << " does not match the local slab width " << d.y << std::endl;
+    exit(-1);
+  }
+  fftx->setTag(1);
+  ffty->setTag(2);
+  scale=1.0/normalization();
+}
+
+void Convolution2MPI::runMPI(Complex **f, size_t offset, double sc)
+{
+  runSlab(fftx,A,B,devF,f,offset,sc,[this](Complex **T, size_t lo, size_t hi) {
+    convolvey[0]->convolveRows(T,lo*d.Y,hi-lo,d.Y,1.0);
+  });
+}
+
+void Convolution2MPI::convolveRaw(Complex **f, size_t offset, Indices *)
+{
+  runMPI(f,offset,1.0);
+}
+
+void Convolution2MPI::convolve(Complex **f, size_t offset)
+{
+  runMPI(f,offset,scale);
+}
+
 Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
                                  const MPIgroup& group) :
-  Convolution3(fftx,ffty,fftz,NULL,NULL,NULL,true), group(group)
+  Convolution3(fftx,ffty,fftz,NULL,NULL,NULL,true), SlabTranspose(group)
 {
   if(fftx->S != fftx->C) {
     std::cerr << "Convolution3MPI: the local x pass must be contiguous (S == C)"
@@ -32,10 +83,6 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
   ffty->setTag(2);
   fftz->setTag(3);
   scale=1.0/normalization();
-  commStream=NULL;
-  nchunks=1;
-  const char *e=getenv("FFTWPP_MPI_CHUNKS");
-  if(e && *e) nchunks=std::max<size_t>(1,strtoull(e,NULL,10));
   // the fused exchange needs both strided passes on the power-of-two
   // register kernels (fast_kernels.cu) and the y pass in its direct variant
   auto pow2ok=[](size_t m) {return m >= 64 && m <= 4096 && (m & (m-1)) == 0;};
@@ -44,7 +91,7 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
     fftx->q > 1 && ffty->q > 1 &&
     (fftx->kind() == fftBase::COMPLEX || fftx->kind() == fftBase::REAL) &&
     fftx->p <= 2;
-  e=getenv("FFTWPP_MPI_FUSED");
+  const char *e=getenv("FFTWPP_MPI_FUSED");
   if(e && *e == '0') fused=false;
   fusedReady=false;
 }
@@ -52,13 +99,11 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
 Convolution3MPI::~Convolution3MPI()
 {
   for(size_t i=0; i < opened.size(); ++i) fftwpp_gpu_ipc_close(opened[i]);
-  for(size_t i=0; i < events.size(); ++i) fftwpp_gpu_event_destroy(events[i]);
-  if(commStream) fftwpp_gpu_stream_destroy(commStream);
 }
 
 // Sub-range [lo,hi) (relative to the rank's first transformed x row) of
 // chunk c of nc for the given rank.
-void Convolution3MPI::chunkRange(int rank, size_t c, size_t nc, size_t *lo,
+void SlabTranspose::chunkRange(int rank, size_t c, size_t nc, size_t *lo,
                                  size_t *hi)
 {
   size_t x=localdimension(d.X,rank,group.size,NULL);
@@ -68,7 +113,7 @@ void Convolution3MPI::chunkRange(int rank, size_t c, size_t nc, size_t *lo,
 
 // direction 0: x-transformed slab (X x y x Z) -> (x x Y x Z)   [localize1]
 // direction 1: the inverse                                     [localize0]
-void Convolution3MPI::exchangeTable(int direction, uint64_t *scount,
+void SlabTranspose::exchangeTable(int direction, uint64_t *scount,
                                     uint64_t *sdispl, uint64_t *rcount,
                                     uint64_t *rdispl, size_t c, size_t nc)
 {
@@ -101,7 +146,7 @@ void Convolution3MPI::exchangeTable(int direction, uint64_t *scount,
   }
 }
 
-void Convolution3MPI::transposeForward(void *Fx, void *T, size_t c, size_t nc,
+void SlabTranspose::transposeForward(void *Fx, void *T, size_t c, size_t nc,
                                        void *st)
 {
   std::vector<uint64_t> sc(group.size),sd(group.size),rc(group.size),
@@ -124,7 +169,7 @@ void Convolution3MPI::transposeForward(void *Fx, void *T, size_t c, size_t nc,
   }
 }
 
-void Convolution3MPI::transposeBackward(void *T, void *Fx, size_t c, size_t nc,
+void SlabTranspose::transposeBackward(void *T, void *Fx, size_t c, size_t nc,
                                         void *st)
 {
   std::vector<uint64_t> sc(group.size),sd(group.size),rc(group.size),
@@ -151,12 +196,14 @@ void Convolution3MPI::transposeBackward(void *T, void *Fx, size_t c, size_t nc,
 //   X:        F(0,c0) F(1,c0) F(0,c1) F(1,c1) ..  B(c0) B(c1) ..
 // F(a,c): forward exchange + unpack of chunk c of array a; B(c): pack +
 // inverse exchange of chunk c of the outputs.
-void Convolution3MPI::runMPI(Complex **f, size_t offset, double sc)
+void SlabTranspose::runSlab(fftBase *fftx, size_t A, size_t B,
+                            DeviceArrays& devF, Complex **f, size_t offset,
+                            double sc, const InnerSweep& inner)
 {
   size_t N=std::max(A,B);
   void *st=gpu::stream();
   if(!gpu::isDevice(f[0])) {
-    std::cerr << "Convolution3MPI needs device pointers" << std::endl;
+    std::cerr << "distributed convolutions need device pointers" << std::endl;
     exit(-1);
   }
   size_t rows=fftx->allRows();
@@ -206,8 +253,7 @@ void Convolution3MPI::runMPI(Complex **f, size_t offset, double sc)
     size_t lo,hi;
     chunkRange(group.rank,c,nc,&lo,&hi);
     gpu::check(fftwpp_gpu_stream_wait_event(st,evF[c]),"wait");
-    if(hi > lo)
-      convolveyz[0]->convolvePlanes(T.data(),lo*d.Y*d.Z,hi-lo,d.Y*d.Z,1.0);
+    if(hi > lo) inner(T.data(),lo,hi);
     gpu::check(fftwpp_gpu_event_record(evY[c],st),"event");
     gpu::check(fftwpp_gpu_stream_wait_event(commStream,evY[c]),"wait");
     for(size_t b=0; b < B; ++b)
@@ -218,6 +264,13 @@ void Convolution3MPI::runMPI(Complex **f, size_t offset, double sc)
   for(size_t b=0; b < B; ++b)
     gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[b],
                                    f[b]+offset,0,sc,1,0,0,st),"backward");
+}
+
+void Convolution3MPI::runMPI(Complex **f, size_t offset, double sc)
+{
+  runSlab(fftx,A,B,devF,f,offset,sc,[this](Complex **T, size_t lo, size_t hi) {
+    convolveyz[0]->convolvePlanes(T,lo*d.Y*d.Z,hi-lo,d.Y*d.Z,1.0);
+  });
 }
 
 // One-time collective setup of the fused exchange: allocate the landing

@@ -1,4 +1,4 @@
-/* mpiconvolve.h -- distributed 3-D hybrid convolution over NCCL.
+/* mpiconvolve.h -- distributed 2-D/3-D hybrid convolutions over NCCL.
  *
  * Mirrors the reference's MPI layer for the slab decomposition
  * (mpi/mpigroup.h:8-167, mpi/mpitranspose.h:118-130, mpi/mpiconvolve.h:182-305):
@@ -9,13 +9,15 @@
  * the local x backward pass.  The adaptive MPI transpose is replaced by one
  * NCCL grouped send/receive per array and direction.
  *
- * Pencil decomposition (Convolution2MPI inside each x row) is only selected by
- * the reference when ranks > Ly (mpigroup.h:33-39); it is not implemented here.
+ * Pencil decomposition (a Convolution2MPI nested inside each x row) is only
+ * selected by the reference when ranks > Ly (mpigroup.h:33-39); it is not
+ * implemented here.  Convolution2MPI itself (2-D data, y split) is.
  */
 #ifndef FFTWPP_B200_MPICONVOLVE_H
 #define FFTWPP_B200_MPICONVOLVE_H
 
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "convolve.h"
@@ -61,10 +63,69 @@ public:
 
 namespace fftwpp {
 
-class Convolution3MPI : public Convolution3 {
+// The slab exchange shared by the distributed convolutions: global data of
+// X transformed x rows by Y rows of Z words; before the exchange every rank
+// holds all X rows of its y slice (X x y x Z), after it all of Y for its slice
+// of x rows (x x Y x Z) -- the reference's mpitranspose localize1/localize0
+// (mpi/mpitranspose.h:163-933) as one NCCL grouped send/receive per array.
+class SlabTranspose {
 public:
   utils::MPIgroup group;
-  utils::split3 d;   // X = fftx->allRows(), Y = Ly, Z = Sy (row length in words)
+  utils::split3 d;
+
+  // byte counts/displacements of the two exchanges (for tests); chunk c of
+  // nchunks restricts every rank's transformed x rows to its c-th sub-range
+  void exchangeTable(int direction, uint64_t *scount, uint64_t *sdispl,
+                     uint64_t *rcount, uint64_t *rdispl, size_t chunk=0,
+                     size_t nchunks=1);
+
+  // Number of x-row chunks the exchanges are pipelined in (overlap of the
+  // all-to-all with the inner sweep, cf. mpi/mpiconvolve.h:125-139); env
+  // FFTWPP_MPI_CHUNKS, default 1 (measured: no gain from chunking).
+  size_t nchunks;
+
+protected:
+  SlabTranspose(const utils::MPIgroup& group);
+  ~SlabTranspose();
+  DeviceArrays devT;   // transposed data: x x Y x Z per array
+  DeviceArrays devP;   // pack/unpack staging
+  void *commStream;
+  std::vector<void *> events;
+  // inner(T,lo,hi): convolve the local transformed x rows [lo,hi) of the
+  // arrays T[a] (x x Y x Z each) in place
+  typedef std::function<void(Complex **T, size_t lo, size_t hi)> InnerSweep;
+  void runSlab(fftBase *fftx, size_t A, size_t B, DeviceArrays& devF,
+               Complex **f, size_t offset, double scale,
+               const InnerSweep& inner);
+  void chunkRange(int rank, size_t c, size_t nc, size_t *lo, size_t *hi);
+  void transposeForward(void *Fx, void *T, size_t c, size_t nc, void *st);
+  void transposeBackward(void *T, void *Fx, size_t c, size_t nc, void *st);
+};
+
+// Distributed 2-D convolution (reference Convolution2MPI,
+// mpi/mpiconvolve.h:72-179): every rank holds all of x and a slice of y.
+class Convolution2MPI : public Convolution2, public SlabTranspose {
+public:
+  // fftx must be built for the LOCAL slab: C = S = d.y; ffty as in the
+  // serial case (tests: mpi/tests/hybridconv2.cc).
+  Convolution2MPI(fftBase *fftx, fftBase *ffty, const utils::MPIgroup& group);
+
+  // f: device pointers to the local slabs (Lx x d.y input words each).
+  void convolveRaw(Complex **f, size_t offset=0, Indices *indices=NULL);
+  void convolve(Complex **f, size_t offset=0);
+
+  size_t stridex() {return d.Y;}
+  size_t blocksizex(size_t) {return d.x;}
+  size_t indexBase() {return d.x0;}
+  size_t inputLengthy() {return d.y;}
+
+protected:
+  void runMPI(Complex **f, size_t offset, double scale);
+};
+
+class Convolution3MPI : public Convolution3, public SlabTranspose {
+public:
+  // d: X = fftx->allRows(), Y = Ly, Z = Sy (row length in words)
 
   // fftx must be built for the LOCAL slab: C = S = d.y*Lz; ffty/fftz as in the
   // serial case (tests: mpi/tests/hybridconvr3.cc:85-102).
@@ -75,17 +136,6 @@ public:
   // f: device pointers to the local slabs (Lx x d.y x Lz input words each).
   void convolveRaw(Complex **f, size_t offset=0, Indices *indices=NULL);
   void convolve(Complex **f, size_t offset=0);
-
-  // byte counts/displacements of the two exchanges (for tests); chunk c of
-  // nchunks restricts every rank's transformed x rows to its c-th sub-range
-  void exchangeTable(int direction, uint64_t *scount, uint64_t *sdispl,
-                     uint64_t *rcount, uint64_t *rdispl, size_t chunk=0,
-                     size_t nchunks=1);
-
-  // Number of x-row chunks the exchanges are pipelined in (overlap of the
-  // all-to-all with the y/z sweep, cf. mpi/mpiconvolve.h:125-139); env
-  // FFTWPP_MPI_CHUNKS, default 4.
-  size_t nchunks;
 
   // Fused exchange: the x forward pass and the y backward pass store their
   // results straight into the owning peer's buffers over NVLink (CUDA IPC
@@ -103,14 +153,7 @@ protected:
   DeviceArrays devMap;         // row maps (base, stride) per array
   void setupFused();
   void runFused(Complex **f, size_t offset, double scale);
-  DeviceArrays devT;   // transposed data: x x Y x Z per array
-  DeviceArrays devP;   // pack/unpack staging
-  void *commStream;
-  std::vector<void *> events;
   void runMPI(Complex **f, size_t offset, double scale);
-  void chunkRange(int rank, size_t c, size_t nc, size_t *lo, size_t *hi);
-  void transposeForward(void *Fx, void *T, size_t c, size_t nc, void *st);
-  void transposeBackward(void *T, void *Fx, size_t c, size_t nc, void *st);
 };
 
 }

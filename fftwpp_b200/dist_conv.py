@@ -1,6 +1,7 @@
-"""Distributed (slab over y) 3-D hybrid convolution: Python handle on the C++
-Convolution3MPI counterpart (cpp/mpiconvolve.h; reference mpi/mpiconvolve.h
-:182-305, driver mpi/tests/hybridconvr3.cc).  One process per GPU;
+"""Distributed (slab over y) 2-D and 3-D hybrid convolutions: Python handles on
+the C++ Convolution2MPI / Convolution3MPI counterparts (cpp/mpiconvolve.h;
+reference mpi/mpiconvolve.h:72-305, drivers mpi/tests/hybridconv2.cc,
+hybridconvr3.cc, hybridconvh3.cc).  One process per GPU;
 torch.distributed is used only to bootstrap the NCCL communicator (broadcast of
 the unique id) -- the exchange itself is issued by lib_fftwpp.so."""
 import ctypes
@@ -18,26 +19,79 @@ def local_dimension(N, rank, size):
     return (n if s + n <= N else N - s), s
 
 
+def _nccl_comm(rank, world):
+    """NCCL communicator of lib_fftwpp.so, bootstrapped over torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    comm = ctypes.c_void_p()
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        rc = lib.fftwpp_gpu_comm_unique_id(buf)
+        if rc:
+            raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    rc = lib.fftwpp_gpu_comm_create(rank, world, raw, ctypes.byref(comm))
+    if rc:
+        raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+    return comm
+
+
+class SlabConvolution2:
+    """2-D complex convolution of Lx x Ly data, y split over the ranks
+    (reference Convolution2MPI, mpi/mpiconvolve.h:72-179)."""
+
+    def __init__(self, Lx, Ly, Mx, My, rank, world, m=None, D=None, I=None, A=2, B=1,
+                 mult=MULT_BINARY, comm="nccl"):
+        self.L, self.M = [Lx, Ly], [Mx, My]
+        self.rank, self.world, self.A, self.B = rank, world, A, B
+        self._comm = _nccl_comm(rank, world) if comm == "nccl" else ctypes.c_void_p()
+        arr, larr = ctypes.c_size_t * 2, ctypes.c_long * 2
+        m = arr(*([0] * 2 if m is None else m))
+        D = arr(*([0] * 2 if D is None else D))
+        I = larr(*([-1] * 2 if I is None else I))
+        self._h = lib.fftwpp_mpiconv2_create(0, arr(*self.L), arr(*self.M), m, D, I,
+                                             A, B, mult, rank, world, self._comm)
+        buf = (ctypes.c_size_t * 9)()
+        lib.fftwpp_mpiconv2_split(self._h, buf)
+        self.split = dict(zip("X Y Z x y z x0 y0 z0".split(), [int(v) for v in buf]))
+
+    def exchange_table(self, direction):
+        n = self.world
+        t = [(ctypes.c_ulonglong * n)() for _ in range(4)]
+        lib.fftwpp_mpiconv2_exchange_table(self._h, direction, *t)
+        return [[int(v) for v in a] for a in t]
+
+    def local_shape(self):
+        return (self.L[0], self.split["y"])
+
+    def convolve(self, arrays, normalized=True):
+        n = max(self.A, self.B)
+        ptrs = (ctypes.c_void_p * n)(*[_ptr(a) for a in arrays[:n]])
+        lib.fftwpp_mpiconv2_convolve(self._h, ptrs, 1 if normalized else 0)
+        return arrays[0]
+
+    def close(self):
+        if self._h:
+            lib.fftwpp_mpiconv2_destroy(self._h)
+            self._h = None
+        if self._comm:
+            lib.fftwpp_gpu_comm_destroy(self._comm)
+            self._comm = ctypes.c_void_p()
+
+
 class SlabConvolution3:
+    """family: FAMILY_COMPLEX, FAMILY_HERMITIAN (local slabs Lx x y x ceil(Lz/2)
+    complex, centred; the caller symmetrises the global field as the
+    reference's HermitianSymmetrizeXY(split3), mpi/mpiconvolve.cc:11-142) or
+    FAMILY_REAL (doubles)."""
+
     def __init__(self, Lx, Ly, Lz, Mx, My, Mz, rank, world, family=FAMILY_REAL,
                  m=None, D=None, I=None, A=2, B=1, mult=MULT_BINARY, comm="nccl"):
         self.L, self.M = [Lx, Ly, Lz], [Mx, My, Mz]
         self.rank, self.world, self.family, self.A, self.B = rank, world, family, A, B
-        self._comm = ctypes.c_void_p()
-        if comm == "nccl":
-            import torch
-            import torch.distributed as dist
-            buf = ctypes.create_string_buffer(128)
-            if rank == 0:
-                rc = lib.fftwpp_gpu_comm_unique_id(buf)
-                if rc:
-                    raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
-            t = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
-            dist.broadcast(t, 0)
-            raw = bytes(t.cpu().tolist())
-            rc = lib.fftwpp_gpu_comm_create(rank, world, raw, ctypes.byref(self._comm))
-            if rc:
-                raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+        self._comm = _nccl_comm(rank, world) if comm == "nccl" else ctypes.c_void_p()
         arr, larr = ctypes.c_size_t * 3, ctypes.c_long * 3
         m = arr(*([0] * 3 if m is None else m))
         D = arr(*([0] * 3 if D is None else D))

@@ -138,7 +138,8 @@ void fftwpp_conv_set_plane_chunk(void *conv, size_t chunk);
 /* ---- distributed (slab over y) 3-D convolution over NCCL: the counterpart
  * of the reference's Convolution3MPI (mpi/mpiconvolve.h:182-305) built as in
  * mpi/tests/hybridconv{,r}3.cc.  comm: handle from fftwpp_gpu_comm_create.
- * family 0 (complex) or 2 (real).  Arrays are the LOCAL slabs
+ * family 0 (complex), 1 (centred Hermitian: last dimension holds the
+ * ceil(Lz/2) non-negative modes) or 2 (real).  Arrays are the LOCAL slabs
  * Lx x y x Lz (device pointers). ---- */
 void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
                              const size_t *m, const size_t *D, const long *I,
@@ -157,6 +158,24 @@ void fftwpp_mpiconv3_exchange_table(void *conv, int direction,
                                     unsigned long long *rcount,
                                     unsigned long long *rdispl);
 void fftwpp_mpiconv3_set_plane_chunk(void *conv, size_t chunk);
+
+/* ---- distributed 2-D convolution: the reference's Convolution2MPI
+ * (mpi/mpiconvolve.h:72-179; driver mpi/tests/hybridconv2.cc).  Arrays are the
+ * LOCAL slabs Lx x y of complex words (family 0); L, M, m, D, I have two
+ * entries.  Same conventions as the 3-D handle. ---- */
+void *fftwpp_mpiconv2_create(int family, const size_t *L, const size_t *M,
+                             const size_t *m, const size_t *D, const long *I,
+                             size_t A, size_t B, int mult, int rank, int size,
+                             void *comm);
+void fftwpp_mpiconv2_destroy(void *conv);
+void fftwpp_mpiconv2_split(void *conv, size_t *out);
+void fftwpp_mpiconv2_params(void *conv, int d, size_t *out);
+void fftwpp_mpiconv2_convolve(void *conv, double **f, int normalized);
+void fftwpp_mpiconv2_exchange_table(void *conv, int direction,
+                                    unsigned long long *scount,
+                                    unsigned long long *sdispl,
+                                    unsigned long long *rcount,
+                                    unsigned long long *rdispl);
 
 /* stream used by every launch issued through this API (a cudaStream_t) */
 void fftwpp_set_stream(void *stream);

@@ -22,32 +22,74 @@ def main():
     fp.lib.fftwpp_gpu_set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
+
+    def report(tag, c, got, want_local, wmax):
+        err = np.max(np.abs(got - want_local)) / max(1.0, wmax)
+        t = torch.tensor([err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(tag, "ranks", world, "split", c.split, "max err", t.item())
+        return t.item() < 1e-12
+
+    def seeded(shape, seed, cplx):
+        rng = np.random.default_rng(seed)       # same global field on every rank
+        a = rng.uniform(-1, 1, shape)
+        return a + 1j * rng.uniform(-1, 1, shape) if cplx else a
+
     cases = [(2, (16, 12, 20)), (2, (33, 9, 8)), (0, (8, 10, 6)), (2, (64, 64, 64))]
     if world > 4:  # every rank needs a non-empty y slab
         # uneven but non-empty slabs: Ly = 3*(world-1)+1 gives ceil-split 3,...,3,1
         cases = [(2, (16, 8 * world, 12)), (0, (9, 3 * (world - 1) + 1, 6)), (2, (64, 64, 64))]
-    for fam, L in cases:
+    # the (64,64,64) case runs the fused (peer-store) exchange; repeat it on the
+    # NCCL all-to-all path
+    runs = [(fam, L, None) for fam, L in cases] + [(2, (64, 64, 64), "0")]
+    for fam, L, fusedenv in runs:
         M = [2 * l for l in L]
+        if fusedenv is not None:
+            os.environ["FFTWPP_MPI_FUSED"] = fusedenv
         c = dist_conv.SlabConvolution3(*L, *M, rank, world, family=fam)
-        f = c.make_inputs(seed=7, scale_second=1.0)
-        # gather the global inputs on every rank (test only)
-        full = []
-        for a in range(2):
-            parts = [None] * world
-            dist.all_gather_object(parts, f[a].cpu().numpy())
-            full.append(np.concatenate(parts, axis=1))
+        os.environ.pop("FFTWPP_MPI_FUSED", None)
+        full = [seeded(L, 7 + a, fam == 0) for a in range(2)]
+        y, y0 = c.split["y"], c.split["y0"]
+        f = [torch.from_numpy(np.ascontiguousarray(a[:, y0:y0 + y, :])).cuda() for a in full]
         want = O.conv_real(full[0], full[1]) if fam == 2 else O.conv_complex(full[0], full[1])
         c.convolve(f)
         torch.cuda.synchronize()
+        tag = "3-D family %d L %s%s" % (fam, L, " (NCCL path)" if fusedenv == "0" else "")
+        ok = report(tag, c, f[0].cpu().numpy(), want[:, y0:y0 + y, :], np.max(np.abs(want))) and ok
+        c.close()
+
+    # centred Hermitian 3-D (reference mpi/tests/hybridconvh3.cc): the global
+    # field is symmetrised, every rank takes its y slice of the half-spectrum
+    for L in ((8, 2 * world + 2, 10), (12, 4 * world, 7)):
+        M = [3 * l // 2 + 1 for l in L]
+        c = dist_conv.SlabConvolution3(*L, *M, rank, world, family=fp.FAMILY_HERMITIAN,
+                                       mult=fp.MULT_REALBINARY)
+        H = (L[2] + 1) // 2
+        full = [seeded((L[0], L[1], H), 17 + a, True) for a in range(2)]
+        for a in full:
+            O.symmetrize(L, a)
         y, y0 = c.split["y"], c.split["y0"]
-        got = f[0].cpu().numpy()
-        ref = want[:, y0:y0 + y, :]
-        err = np.max(np.abs(got - ref)) / max(1.0, np.max(np.abs(want)))
-        t = torch.tensor([err], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            print("family", fam, "L", L, "ranks", world, "split", c.split, "max err", t.item())
-        ok = ok and t.item() < 1e-12
+        f = [torch.from_numpy(np.ascontiguousarray(a[:, y0:y0 + y, :])).cuda() for a in full]
+        want = O.conv_hermitian(L, full[0], full[1])
+        c.convolve(f)
+        torch.cuda.synchronize()
+        ok = report("3-D Hermitian L %s" % (L,), c, f[0].cpu().numpy(),
+                    want[:, y0:y0 + y, :], np.max(np.abs(want))) and ok
+        c.close()
+
+    # 2-D complex (reference Convolution2MPI, mpi/tests/hybridconv2.cc)
+    for L in ((16, 4 * world), (33, 3 * (world - 1) + 1), (128, 64 * world)):
+        M = [2 * l for l in L]
+        c = dist_conv.SlabConvolution2(*L, *M, rank, world)
+        full = [seeded(L, 27 + a, True) for a in range(2)]
+        y, y0 = c.split["y"], c.split["y0"]
+        f = [torch.from_numpy(np.ascontiguousarray(a[:, y0:y0 + y])).cuda() for a in full]
+        want = O.conv_complex(full[0], full[1])
+        c.convolve(f)
+        torch.cuda.synchronize()
+        ok = report("2-D complex L %s" % (L,), c, f[0].cpu().numpy(), want[:, y0:y0 + y],
+                    np.max(np.abs(want))) and ok
         c.close()
     dist.destroy_process_group()
     if not ok:

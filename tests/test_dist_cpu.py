@@ -1,5 +1,5 @@
-"""CPU, world_size 2 over gloo: the byte counts / displacements the C++
-Convolution3MPI computes for its two exchanges (cpp/mpiconvolve.cc) must realise
+"""CPU, world_size 2 and 3 over gloo: the byte counts / displacements the C++
+Convolution2MPI / Convolution3MPI compute for its two exchanges (cpp/mpiconvolve.cc) must realise
 the global (X x y) <-> (x x Y) block transpose of the reference's
 mpitranspose localize1/localize0 (mpi/mpitranspose.h:632-931), including uneven
 splits.  The exchange is emulated with torch.distributed all_to_all-style
@@ -25,8 +25,20 @@ WORKER = textwrap.dedent("""
 
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo")
-    for (Lx, Ly, Lz) in ((8, 6, 4), (7, 5, 3), (16, 9, 2)):
-        c = dist_conv.SlabConvolution3(Lx, Ly, Lz, 2*Lx, 2*Ly, 2*Lz, rank, world, comm=None)
+    cases = [(3, 2, (8, 6, 4)), (3, 2, (7, 5, 3)), (3, 2, (16, 9, 2)), (3, 0, (5, 7, 3)),
+             (3, 1, (8, 6, 10)),               # centred Hermitian: Z = ceil(Lz/2) modes
+             (2, 0, (8, 6)), (2, 0, (9, 7))]   # Convolution2MPI: Z = 1
+    for dim, fam, L in cases:
+        if dim == 3:
+            Lx, Ly, Lz = L
+            M = [2*l for l in L] if fam != 1 else [3*l//2 for l in L]
+            c = dist_conv.SlabConvolution3(Lx, Ly, Lz, *M, rank, world, family=fam,
+                                           mult=2 if fam == 1 else 1, comm=None)
+            assert c.split["Z"] == ((Lz + 1)//2 if fam == 1 else Lz)
+        else:
+            Lx, Ly = L
+            c = dist_conv.SlabConvolution2(Lx, Ly, 2*Lx, 2*Ly, rank, world, comm=None)
+            assert c.split["Z"] == 1
         d = c.split
         X, Y, Z = d["X"], d["Y"], d["Z"]
         ext, st = dist_conv.local_dimension(Ly, rank, world)
