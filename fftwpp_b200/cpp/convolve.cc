@@ -792,9 +792,9 @@ void fftPadHermitian::init()
     callTable.push_back(c);
     totalRows=m;
   } else {
-    if(p != 2) {
-      std::cerr << "fftPadHermitian: only p=2 (or explicit padding) is "
-                << "implemented on the GPU path; got p=" << p << std::endl;
+    if(p % 2 != 0) {
+      std::cerr << "Odd values of p are incompatible with the centered and "
+                << "Hermitian routines." << std::endl;
       invalid();
     }
     dr=Dr();
@@ -807,21 +807,32 @@ void fftPadHermitian::init()
     D0=n % D;
     if(D0 == 0) D0=D;
     const size_t stride=blocksize(0);
+    const size_t N=m*q;
     for(size_t r=0; r < R; r += increment(r)) {
       size_t blocks=(r == 0) ? D0 : D;
       ResidueCall c={r,sub.size(),0,0,totalRows};
       for(size_t d=0; d < blocks; ++d) {
-        SubBlockHost h;
-        memset(&h,0,sizeof(h));
-        h.s.mlen=(uint32_t) m;
-        h.s.nout=(uint32_t) m;
-        h.s.k0=index(r,stride*d);
-        h.s.off_call=2*b*d;       // doubles
-        h.s.off_all=C*totalRows;  // doubles
-        sub.push_back(h);
-        totalRows += m;
-        c.rows += m;
-        ++c.nsb;
+        // p > 2 (reference forwardInner, convolve.cc:5014-5230): p/2 real
+        // blocks of m outputs per residue, one per inner index u
+        for(size_t u=0; u < p2; ++u) {
+          size_t i0=stride*d+u*m;
+          SubBlockHost h;
+          memset(&h,0,sizeof(h));
+          h.s.mlen=(uint32_t) m;
+          h.s.nout=(uint32_t) m;
+          h.s.k0=index(r,i0);
+          if(m > 1 && index(r,i0+1) != (h.s.k0+q) % N) {
+            std::cerr << "internal error: Hermitian residue layout mismatch at"
+                      << " r=" << r << " i=" << i0 << std::endl;
+            exit(-1);
+          }
+          h.s.off_call=2*b*d+C*m*u; // doubles
+          h.s.off_all=C*totalRows;  // doubles
+          sub.push_back(h);
+          totalRows += m;
+          c.rows += m;
+          ++c.nsb;
+        }
       }
       callTable.push_back(c);
     }
@@ -897,60 +908,72 @@ void fftPadReal::init()
     callTable.push_back(c);
     totalRows=e;
   } else {
-    if(p > 2) {
-      std::cerr << "fftPadReal: only p<=2 (or explicit padding) is "
-                << "implemented on the GPU path; got p=" << p << std::endl;
-      invalid();
-    }
-    l=m;
+    const size_t P=p == 2 ? 1 : p;
+    const size_t N=m*q;
+    l=m*P;
     b=S*l;
     dr=Dr();
     R=residueBlocks();
     D0=((n-1)/2) % D;
     if(D0 == 0) D0=D;
+    // Position i of a call holds the reference's value at index(r,i), which
+    // for real data equals the sign +1 transform at k_i=(N-index(r,i)) mod N
+    // (reference tests/hybridr.cc:88-90).  Apart from the r2c block of
+    // p <= 2, every block is a natural-order sub-block: k_i=k0+(N/mlen)*s.
+    auto add=[&](ResidueCall& c, size_t r, size_t i0, size_t mlen,
+                 uint32_t flags) {
+      SubBlockHost h;
+      memset(&h,0,sizeof(h));
+      h.s.mlen=(uint32_t) mlen;
+      h.s.nout=(uint32_t) mlen;
+      h.s.flags=flags;
+      size_t k0=(N-index(r,i0)) % N;
+      if(mlen > 1 && (N-index(r,i0+1)) % N != (k0+N/mlen) % N) {
+        std::cerr << "internal error: real residue layout mismatch at r=" << r
+                  << " i=" << i0 << std::endl;
+        exit(-1);
+      }
+      h.s.k0=k0;
+      h.s.off_call=S*i0;
+      h.s.off_all=S*totalRows;
+      sub.push_back(h);
+      totalRows += mlen;
+      c.rows += mlen;
+      ++c.nsb;
+    };
     for(size_t r=0; r < R; r += increment(r)) {
       ResidueCall c={r,sub.size(),0,0,totalRows};
       if(r == 0) {
-        SubBlockHost h;
-        memset(&h,0,sizeof(h));
-        h.s.mlen=(uint32_t) m;
-        h.s.nout=(uint32_t) e;
-        h.s.flags=FFTWPP_SB_CONJ_OUT;
-        h.s.k0=0;
-        h.s.off_call=0;
-        h.s.off_all=S*totalRows;
-        sub.push_back(h);
-        totalRows += e;
-        c.rows += e;
-        ++c.nsb;
-      } else if(2*r < q) {
-        size_t blocks=(r == 1) ? D0 : D;
-        for(size_t d=0; d < blocks; ++d) {
+        if(p <= 2) { // r2c: e outputs stored with the sign -1 convention
           SubBlockHost h;
           memset(&h,0,sizeof(h));
           h.s.mlen=(uint32_t) m;
-          h.s.nout=(uint32_t) m;
-          h.s.k0=r+d;
-          h.s.off_call=b*d;
+          h.s.nout=(uint32_t) e;
+          h.s.flags=FFTWPP_SB_CONJ_OUT;
+          h.s.k0=0;
+          h.s.off_call=0;
           h.s.off_all=S*totalRows;
           sub.push_back(h);
-          totalRows += m;
-          c.rows += m;
+          totalRows += e;
+          c.rows += e;
           ++c.nsb;
+        } else {
+          // residues -u*n, u <= p/2 (reference forwardInner,
+          // convolve.cc:6168-6330): u=0 holds both halves of its spectrum;
+          // for even p the class 2u == p is the packed half-length one
+          for(size_t u=0; u < ceilquotient(p,2); ++u)
+            add(c,0,u*m,m,u == 0 ? FFTWPP_SB_SELFCONJ : 0);
+          if(p % 2 == 0) add(c,0,(p/2)*m,e-1,0);
         }
-      } else { // 2r == q: packed half-length class
-        size_t h2=e-1;
-        SubBlockHost h;
-        memset(&h,0,sizeof(h));
-        h.s.mlen=(uint32_t) h2;
-        h.s.nout=(uint32_t) h2;
-        h.s.k0=r;
-        h.s.off_call=0;
-        h.s.off_all=S*totalRows;
-        sub.push_back(h);
-        totalRows += h2;
-        c.rows += h2;
-        ++c.nsb;
+      } else if(2*r == n) {
+        if(p <= 2) add(c,r,0,e-1,0);  // packed half-length class
+        else
+          for(size_t u=0; u < p/2; ++u) add(c,r,u*m,m,0);
+      } else {
+        size_t blocks=(r == 1) ? D0 : D;
+        for(size_t d=0; d < blocks; ++d)
+          for(size_t u=0; u < P; ++u)
+            add(c,r,d*l+u*m,m,0);
       }
       callTable.push_back(c);
     }

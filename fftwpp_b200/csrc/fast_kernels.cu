@@ -1308,7 +1308,8 @@ __device__ __forceinline__ void backwardSub(const PlanDev& P,
           int idx=(j-shift)*T+lane;
           if(KIND == FFTWPP_KIND_REAL) {
             double *a=(double *) acc;
-            a[idx] += (sb.flags & FFTWPP_SB_CONJ_OUT) ? v.x : 2.0*v.x;
+            a[idx] += (sb.flags & (FFTWPP_SB_CONJ_OUT | FFTWPP_SB_SELFCONJ))
+          ? v.x : 2.0*v.x;
           } else {
             double2 *a=(double2 *) acc;
             a[idx]=a[idx]+v;

@@ -406,7 +406,8 @@ __device__ void accumulate(const PlanDev& P, const SubBlockDev& sb,
     }
     if(KIND == FFTWPP_KIND_REAL) {
       double *a=(double *) acc;
-      a[idx] += (sb.flags & FFTWPP_SB_CONJ_OUT) ? v.x : 2.0*v.x;
+      a[idx] += (sb.flags & (FFTWPP_SB_CONJ_OUT | FFTWPP_SB_SELFCONJ))
+          ? v.x : 2.0*v.x;
     } else {
       double2 *a=(double2 *) acc;
       a[idx]=cadd(a[idx],v);

@@ -61,6 +61,10 @@ extern "C" {
 /* Sub-block flags. */
 #define FFTWPP_SB_CONJ_OUT 1u  /* store conj(FFT): r2c (sign -1) convention of
                                   the r=0 block of fftPadReal */
+#define FFTWPP_SB_SELFCONJ 2u  /* fftPadReal, p > 2: the block holds both halves
+                                  of a conjugate-symmetric spectrum (r=0, u=0),
+                                  so the backward pass adds Re() once instead of
+                                  twice */
 
 /* One FFT sub-block of a residue pass.  The forward pass computes
  *   W[s] = sum_{j in [jmin,jmax), j = s (mod mlen)} zeta_N^{k0*j} * g(j)

@@ -84,17 +84,40 @@ def index_complex(r, i, *, m, p, q, n, D, D0, centered):
 
 
 def index_real(r, i, *, m, p, q, n):
-    """fftPadReal::index for p <= 2 (convolve.h:956-979)."""
+    """fftPadReal::index (convolve.h:956-979), including the inner (p > 2)
+    layouts."""
     if q == 1:
         return i
     s = i % m
     P = 1 if p == 2 else p
     r += i // (P * m)
-    if r == 0:
-        return q * i
-    if 2 * r == q:
-        return q * m - (q * 2 * i + r)
+    if p <= 2:
+        if r == 0:
+            return q * i
+        if 2 * r == q:
+            return q * m - (q * 2 * i + r)
+    else:
+        u = (i // m) % p
+        if r == 0:
+            if 2 * u == p:
+                return q * m - (q * 2 * s + u * n)
+            return u * n if s == 0 else q * m - (q * s - u * n)
+        if 2 * r == n:
+            return q * m - (q * s + 2 * u * n + r)
+        return q * (m - s) - (u * n + r)
     return q * (m - s) - r
+
+
+def real_blocksize(r, *, m, p, n):
+    """fftPadReal::blocksize (convolve.h:941-945)."""
+    e = m // 2 + 1
+    if r == 0:
+        if p > 2:
+            return (p // 2 + 1) * m if p % 2 else (p // 2) * m + e - 1
+        return e
+    if 2 * r == n:
+        return (p // 2) * m if p > 2 else e - 1
+    return m * (1 if p == 2 else p)
 
 
 # --------------------------------------------------------------------------

@@ -64,8 +64,6 @@ def pad_sweep():
                         p, n, q = O.parameters(L, M, m, kind in (1, 2))
                         if q * m < M:
                             continue
-                        if q > 1 and p > 2 and kind in (2, 3):
-                            continue
                         if kind == 1 and q > 1 and p % 2:
                             continue
                         for D in valid_D(kind, m, p, q, n, S, C):
@@ -110,6 +108,12 @@ def conv_cases():
         ("h2", 1, [8, 6], [12, 9], None, None, None),
         ("h2_odd", 1, [7, 5], [11, 8], None, None, None),
         ("h3", 1, [6, 5, 8], [9, 8, 12], None, None, None),
+        # inner (p > 2) routines of the real and Hermitian classes
+        ("r1_inner_even", 2, [16], [32], [4], [1], [0]),
+        ("r1_inner_odd", 2, [12], [36], [4], [1], [0]),
+        ("r2_inner", 2, [12, 6], [36, 12], [4, 6], [1, 1], [0, 0]),
+        ("h1_inner", 1, [16], [24], [4], [2], [0]),
+        ("h2_inner", 1, [8, 16], [12, 24], [4, 4], [1, 2], [0, 0]),
     ]
     meta = []
     for name, fam, L, M, m, D, I in cases:
@@ -167,6 +171,11 @@ def forward_cases():
         ("real_p1_D", 3, 8, 40, 1, 1, 8, 2),
         ("real_p2", 3, 8, 16, 1, 1, 4, 1),
         ("real_many", 3, 6, 12, 2, 3, 6, 1),
+        ("herm_inner", 2, 16, 24, 1, 1, 4, 2),
+        ("real_inner_even", 3, 16, 32, 1, 1, 4, 1),
+        ("real_inner_odd", 3, 12, 36, 1, 1, 4, 1),
+        ("real_inner_D2", 3, 12, 60, 1, 1, 4, 2),
+        ("real_inner_many", 3, 12, 36, 2, 3, 4, 1),
     ]
     for name, kind, L, M, C, S, m, D in cases:
         b = R.RefPad(kind, L, M, C, S, m, D, 0, A=1, B=1)

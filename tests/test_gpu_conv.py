@@ -51,7 +51,7 @@ def test_conv1d_complex_auto(L):
 def _forced_1d(kind_family):
     out = []
     centered = kind_family == fp.FAMILY_HERMITIAN
-    for L in (3, 5, 7, 8, 12, 16):
+    for L in (3, 5, 7, 8, 12, 16, 24):
         Ms = [2 * L, 5 * L // 2, 3 * L] if not centered else [(3 * L + 1) // 2, 2 * L, 3 * L]
         for M in Ms:
             for m in sorted(set([M, L + 1, L, (L + 1) // 2, max(2, L // 4)])):
@@ -65,14 +65,12 @@ def _forced_1d(kind_family):
                 elif kind_family == fp.FAMILY_HERMITIAN:
                     if q == 1:
                         Ds = [1]
-                    elif p == 2:
-                        Ds = [2]
+                    elif p % 2 == 0:
+                        Ds = [2]  # p > 2: the inner routines (C == 1)
                     else:
                         continue
                 else:
-                    if q > 1 and p > 2:
-                        continue
-                    if not ((n % 2 == 1 or p <= 2) and (q % 2 == 1 or m % 2 == 0)):
+                    if not ((n % 2 == 1 or p % 2 == 0 or p <= 2) and (q % 2 == 1 or m % 2 == 0)):
                         continue
                     Ds = [1]
                     if (n - 1) // 2 > 1:

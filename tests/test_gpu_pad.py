@@ -44,8 +44,6 @@ def cases():
                         p, n, q = O.parameters(L, M, m, kind in (1, 2))
                         if q * m < M:
                             continue
-                        if q > 1 and p > 2 and kind in (2, 3):
-                            continue
                         if kind == 1 and q > 1 and p % 2:
                             continue
                         for D in _valid_D(kind, m, p, q, n, S, C):

@@ -84,19 +84,17 @@ def test_padded_dft_and_index_match_reference_forward(case):
             b = F.shape[0] // D
             Fr = F.view(np.float64)
             blocks = D0 if r == 0 else D
+            stride = m * (1 if q == 1 else p // 2)  # blocksize (convolve.h:786-793)
             for d in range(blocks):
-                for k in range(m):
-                    i = O.index_complex(r, k + m * d, m=m, p=p, q=q, n=n, D=D, D0=D0,
+                for k in range(stride):
+                    i = O.index_complex(r, k + stride * d, m=m, p=p, q=q, n=n, D=D, D0=D0,
                                         centered=True)
                     got = Fr[2 * b * d + C * k: 2 * b * d + C * k + C]
                     assert np.allclose(got, F2[i], rtol=0, atol=1e-12 * max(1, np.abs(F2).max()))
         elif kind == 3:
-            if r == 0:
-                nout = e
-            elif 2 * r == n:
-                nout = e - 1
-            else:
-                nout = m * (D0 if r == 1 else D)
+            nout = O.real_blocksize(r, m=m, p=p, n=n)
+            if r > 0 and 2 * r != n:
+                nout *= D0 if r == 1 else D
             for k in range(nout):
                 i = O.index_real(r, k, m=m, p=p, q=q, n=n)
                 val = np.array([O.real_spectrum_at(F2[:, c], N, i) for c in range(C)])
