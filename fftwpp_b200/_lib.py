@@ -103,4 +103,10 @@ _sig("fftwpp_mpiconv2_params", None, c_void_p, c_int, P(c_size_t))
 _sig("fftwpp_mpiconv2_convolve", None, c_void_p, P(c_void_p), c_int)
 _sig("fftwpp_mpiconv2_exchange_table", None, c_void_p, c_int, P(ctypes.c_ulonglong),
      P(ctypes.c_ulonglong), P(ctypes.c_ulonglong), P(ctypes.c_ulonglong))
+HOST_MULT = ctypes.CFUNCTYPE(None, P(c_void_p), c_size_t, c_void_p, c_size_t)
+DEVICE_MULT = ctypes.CFUNCTYPE(None, P(c_void_p), c_size_t, c_void_p, c_void_p)
+_sig("fftwpp_conv_create_custom", c_void_p, c_int, c_int, P(c_size_t), P(c_size_t),
+     P(c_size_t), P(c_size_t), P(c_long), c_size_t, c_size_t, c_size_t, c_size_t,
+     HOST_MULT, DEVICE_MULT)
+_sig("fftwpp_indices_get", None, c_void_p, P(c_size_t), P(c_size_t))
 _sig("fftwpp_conv_convolve_rows", None, c_void_p, P(c_void_p), c_size_t, c_size_t, c_int)

@@ -112,7 +112,14 @@ class HybridConv:
     """
 
     def __init__(self, L, M=None, family=FAMILY_COMPLEX, m=None, D=None, I=None,
-                 Sx=0, Sy=0, A=2, B=1, mult=None):
+                 Sx=0, Sy=0, A=2, B=1, mult=None, device_mult=None):
+        """mult: one of the MULT_* built-ins (fused on the GPU), or a Python
+        callable mult(F, n, r, offset) -- the reference's user `multiplier`
+        (convolve.h:78-82): F is a list of max(A,B) numpy views of the n
+        transformed words of one residue block, results go to F[0:B].
+        device_mult (with a callable mult): device_mult(ptrs, n, r, offset,
+        stream) receives the DEVICE addresses of the same blocks and must only
+        enqueue GPU work; the transformed data then stays on the GPU."""
         L = [int(v) for v in (L if hasattr(L, "__len__") else [L])]
         dim = len(L)
         if M is None:
@@ -129,9 +136,38 @@ class HybridConv:
         D = arr(*([0] * dim if D is None else [int(v) for v in D]))
         I = larr(*([-1] * dim if I is None else [int(v) for v in I]))
         self.dim, self.family, self.L, self.M, self.A, self.B = dim, family, L, M, A, B
-        self._h = lib.fftwpp_conv_create(dim, family, arr(*L), arr(*M), m, D, I,
-                                         Sx, Sy, A, B, mult)
+        if callable(mult):
+            self._cb = self._callbacks(mult, device_mult, family, max(A, B))
+            self._h = lib.fftwpp_conv_create_custom(dim, family, arr(*L), arr(*M), m, D, I,
+                                                    Sx, Sy, A, B, *self._cb)
+        else:
+            self._h = lib.fftwpp_conv_create(dim, family, arr(*L), arr(*M), m, D, I,
+                                             Sx, Sy, A, B, mult)
         self.doubles = int(lib.fftwpp_conv_doubles(self._h))
+
+    @staticmethod
+    def _callbacks(mult, device_mult, family, narrays):
+        """ctypes thunks for a Python multiplier pair (kept alive by the object)."""
+        import numpy as np
+        from ._lib import HOST_MULT, DEVICE_MULT
+        dtype = np.float64 if family == FAMILY_HERMITIAN else np.complex128
+
+        def context(indices):
+            r, off = ctypes.c_size_t(), ctypes.c_size_t()
+            lib.fftwpp_indices_get(indices, ctypes.byref(r), ctypes.byref(off))
+            return int(r.value), int(off.value)
+
+        def host(F, n, indices, threads):
+            views = [np.ctypeslib.as_array(ctypes.cast(F[a], ctypes.POINTER(ctypes.c_double)),
+                                           shape=(n * (dtype().itemsize // 8),)).view(dtype)
+                     for a in range(narrays)]
+            mult(views, n, *context(indices))
+
+        def device(F, n, indices, stream):
+            device_mult([int(F[a]) for a in range(narrays)], n, *context(indices), stream)
+
+        return (HOST_MULT(host),
+                DEVICE_MULT(device) if device_mult else ctypes.cast(None, DEVICE_MULT))
 
     def close(self):
         if self._h:

@@ -85,7 +85,7 @@ struct Conv {
 
 Conv *makeConv(int dim, int family, const size_t *L, const size_t *M,
                const size_t *m, const size_t *D, const long *I, size_t Sx,
-               size_t Sy, size_t A, size_t B, int mult)
+               size_t Sy, size_t A, size_t B, multiplier *mult)
 {
   if(dim < 1 || dim > 3) {
     std::cerr << "dimension must be 1, 2 or 3" << std::endl;
@@ -109,7 +109,7 @@ Conv *makeConv(int dim, int family, const size_t *L, const size_t *M,
   if(!D) D=zero;
   if(!I) I=minus;
   for(int d=0; d < dim; ++d) {
-    multiplier *mu=(d == dim-1) ? pickMult(mult) : multNone;
+    multiplier *mu=(d == dim-1) ? mult : multNone;
     long Id=m[d] > 0 ? I[d] : -1;
     if(d == 0)
       c->app[d]=new Application(A,B,mu,fftw::maxthreads,false,m[d],D[d],Id);
@@ -148,7 +148,8 @@ Conv *simpleConv(int dim, int family, size_t Lx, size_t Ly, size_t Lz)
   size_t M[3];
   for(int d=0; d < dim; ++d)
     M[d]=family == 1 ? defaultMh(L[d]) : defaultM(L[d],2);
-  return makeConv(dim,family,L,M,NULL,NULL,NULL,0,0,2,1,family == 1 ? 2 : 1);
+  return makeConv(dim,family,L,M,NULL,NULL,NULL,0,0,2,1,
+                  pickMult(family == 1 ? 2 : 1));
 }
 
 void binary(Conv *c, fftwpp_cplx *a, fftwpp_cplx *b)
@@ -334,7 +335,30 @@ void *fftwpp_conv_create(int dim, int family, const size_t *L, const size_t *M,
                          const size_t *m, const size_t *D, const long *I,
                          size_t Sx, size_t Sy, size_t A, size_t B, int mult)
 {
-  return makeConv(dim,family,L,M,m,D,I,Sx,Sy,A,B,mult);
+  return makeConv(dim,family,L,M,m,D,I,Sx,Sy,A,B,pickMult(mult));
+}
+
+void *fftwpp_conv_create_custom(int dim, int family, const size_t *L,
+                                const size_t *M, const size_t *m,
+                                const size_t *D, const long *I, size_t Sx,
+                                size_t Sy, size_t A, size_t B,
+                                fftwpp_multiplier *host,
+                                fftwpp_device_multiplier *device)
+{
+  if(!host) {
+    std::cerr << "fftwpp_conv_create_custom: a host multiplier is required "
+              << "(its address identifies the device one)" << std::endl;
+    exit(-1);
+  }
+  registerDeviceMultiplier((multiplier *) host,(deviceMultiplier *) device);
+  return makeConv(dim,family,L,M,m,D,I,Sx,Sy,A,B,(multiplier *) host);
+}
+
+void fftwpp_indices_get(void *indices, size_t *r, size_t *offset)
+{
+  Indices *i=(Indices *) indices;
+  if(r) *r=i->r;
+  if(offset) *offset=i->offset;
 }
 
 void fftwpp_conv_destroy(void *conv) {delete (Conv *) conv;}

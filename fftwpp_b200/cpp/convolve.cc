@@ -166,6 +166,34 @@ static int multiplierId(multiplier *mult)
   return -1; // custom host multiplier: unfused path
 }
 
+namespace {
+std::vector<std::pair<multiplier *,deviceMultiplier *> >& deviceMultipliers()
+{
+  static std::vector<std::pair<multiplier *,deviceMultiplier *> > table;
+  return table;
+}
+}
+
+void registerDeviceMultiplier(multiplier *host, deviceMultiplier *device)
+{
+  auto& t=deviceMultipliers();
+  for(size_t i=0; i < t.size(); ++i)
+    if(t[i].first == host) {
+      if(device) t[i].second=device;
+      else t.erase(t.begin()+i);
+      return;
+    }
+  if(device) t.push_back(std::make_pair(host,device));
+}
+
+deviceMultiplier *deviceMultiplierOf(multiplier *host)
+{
+  auto& t=deviceMultipliers();
+  for(size_t i=0; i < t.size(); ++i)
+    if(t[i].first == host) return t[i].second;
+  return NULL;
+}
+
 void Indices::copy(Indices *indices, size_t size0)
 {
   size=indices ? indices->size : size0;
@@ -1042,6 +1070,11 @@ void Convolution::convolveRows(Complex **f, size_t offset, size_t nrows,
 // Unfused path for user-supplied host multipliers: forward every residue on
 // the GPU, run the multiplier on the host exactly as Convolution::operate does
 // (reference convolve.h:1120-1135), transform back on the GPU.
+// User multipliers are not fused: GPU forward of every residue -> multiplier
+// per residue block (reference operate(), convolve.h:1120-1135) -> GPU
+// backward.  With a registered device implementation the transformed data
+// never leaves the GPU and nothing synchronises; otherwise the blocks make a
+// round trip through host memory for the host function.
 void Convolution::runCustom(Complex **f, size_t offset, size_t nrows,
                             size_t rowstride, double sc)
 {
@@ -1049,11 +1082,13 @@ void Convolution::runCustom(Complex **f, size_t offset, size_t nrows,
   bool herm=fft->kind() == fftBase::HERMITIAN;
   size_t words=fft->allSize();
   size_t wbytes=herm ? sizeof(double) : sizeof(Complex);
+  deviceMultiplier *dmult=deviceMultiplierOf(mult);
   DeviceArrays F;
   F.ensure(N,words*wbytes);
-  std::vector<Complex *> hostF(N);
-  for(size_t a=0; a < N; ++a)
-    hostF[a]=(Complex *) malloc(words*wbytes);
+  std::vector<Complex *> hostF(N,(Complex *) NULL);
+  if(!dmult)
+    for(size_t a=0; a < N; ++a)
+      hostF[a]=(Complex *) malloc(words*wbytes);
   const std::vector<ResidueCall>& calls=fft->calls();
   size_t nsub=calls.back().sb0+calls.back().nsb;
   void *st=gpu::stream();
@@ -1067,10 +1102,11 @@ void Convolution::runCustom(Complex **f, size_t offset, size_t nrows,
     for(size_t a=0; a < A; ++a) {
       gpu::check(fftwpp_gpu_forward(fft->plan(),0,nsub,1,f[a]+off,F.ptr[a],
                                     1,0,0,st),"forward");
-      gpu::check(fftwpp_gpu_memcpy_d2h(hostF[a],F.ptr[a],words*wbytes,st),
-                 "d2h");
+      if(!dmult)
+        gpu::check(fftwpp_gpu_memcpy_d2h(hostF[a],F.ptr[a],words*wbytes,st),
+                   "d2h");
     }
-    gpu::check(fftwpp_gpu_stream_sync(st),"sync");
+    if(!dmult) gpu::check(fftwpp_gpu_stream_sync(st),"sync");
     std::vector<Complex *> G(N);
     for(size_t ic=0; ic < calls.size(); ++ic) {
       const ResidueCall& c=calls[ic];
@@ -1080,24 +1116,30 @@ void Convolution::runCustom(Complex **f, size_t offset, size_t nrows,
       size_t d=0;
       while(done < c.rows) {
         size_t rowsHere=std::min(bs,c.rows-done);
-        for(size_t a=0; a < N; ++a)
-          G[a]=herm ? (Complex *) ((double *) hostF[a]+fft->C*(c.row0+done))
-            : hostF[a]+fft->S*(c.row0+done);
+        for(size_t a=0; a < N; ++a) {
+          Complex *base=dmult ? (Complex *) F.ptr[a] : hostF[a];
+          G[a]=herm ? (Complex *) ((double *) base+fft->C*(c.row0+done))
+            : base+fft->S*(c.row0+done);
+        }
         indices.r=c.r;
         indices.offset=d*fft->b;
-        (*mult)(G.data(),rowsHere,&indices,threads);
+        if(dmult) (*dmult)(G.data(),rowsHere,&indices,st);
+        else (*mult)(G.data(),rowsHere,&indices,threads);
         done += rowsHere;
         ++d;
       }
     }
     for(size_t bq=0; bq < B; ++bq) {
-      gpu::check(fftwpp_gpu_memcpy_h2d(F.ptr[bq],hostF[bq],words*wbytes,st),
-                 "h2d");
+      if(!dmult)
+        gpu::check(fftwpp_gpu_memcpy_h2d(F.ptr[bq],hostF[bq],words*wbytes,st),
+                   "h2d");
       gpu::check(fftwpp_gpu_backward(fft->plan(),0,nsub,1,F.ptr[bq],
                                      f[bq]+off,0,sc,1,0,0,st),"backward");
     }
-    gpu::check(fftwpp_gpu_stream_sync(st),"sync");
+    if(!dmult) gpu::check(fftwpp_gpu_stream_sync(st),"sync");
   }
+  // F is released at scope exit: the stream must have drained it first
+  if(dmult) gpu::check(fftwpp_gpu_stream_sync(st),"sync");
   for(size_t a=0; a < N; ++a) free(hostF[a]);
 }
 

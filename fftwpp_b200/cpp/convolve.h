@@ -116,6 +116,21 @@ typedef void multiplier(Complex **F, size_t n, Indices *indices,
 // the unfused custom-multiplier path.
 multiplier multNone,multBinary,realMultBinary,multcorrelation;
 
+// Device-side implementation of a user multiplier: same contract as
+// `multiplier` (reference convolve.h:78-82), but F[a] are DEVICE pointers to
+// the n transformed words of one residue block and the function must only
+// ENQUEUE its work (kernel launches) on `stream` (a cudaStream_t).  Without
+// one, a user multiplier runs on the host between a GPU forward and a GPU
+// backward pass, with a device<->host round trip of the transformed data.
+typedef void deviceMultiplier(Complex **F, size_t n, Indices *indices,
+                              void *stream);
+
+// Associate a device implementation with the address of a host multiplier:
+// every Application constructed with `host` then multiplies on the GPU.
+// Passing device=NULL removes the association.
+void registerDeviceMultiplier(multiplier *host, deviceMultiplier *device);
+deviceMultiplier *deviceMultiplierOf(multiplier *host);
+
 class Application : public ThreadBase {
 public:
   size_t A;

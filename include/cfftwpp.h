@@ -118,6 +118,25 @@ void fftwpp_pad_backward(void *pad, const double *F, double *f, size_t r);
 void *fftwpp_conv_create(int dim, int family, const size_t *L, const size_t *M,
                          const size_t *m, const size_t *D, const long *I,
                          size_t Sx, size_t Sy, size_t A, size_t B, int mult);
+
+/* User multipliers (the reference's `multiplier` callback, convolve.h:78-82,
+ * passed to Application): F[a] points at the n transformed words (complex, or
+ * doubles for Hermitian families) of one residue block of array a; results go
+ * to F[0..B).  `host` runs on the CPU between a GPU forward and a GPU backward
+ * pass.  `device` (optional) receives DEVICE pointers instead and must only
+ * enqueue work on `stream` (a cudaStream_t): the transformed data then never
+ * leaves the GPU.  fftwpp_indices_get reads the residue context. */
+typedef void fftwpp_multiplier(double **F, size_t n, void *indices,
+                               size_t threads);
+typedef void fftwpp_device_multiplier(double **F, size_t n, void *indices,
+                                      void *stream);
+void *fftwpp_conv_create_custom(int dim, int family, const size_t *L,
+                                const size_t *M, const size_t *m,
+                                const size_t *D, const long *I, size_t Sx,
+                                size_t Sy, size_t A, size_t B,
+                                fftwpp_multiplier *host,
+                                fftwpp_device_multiplier *device);
+void fftwpp_indices_get(void *indices, size_t *r, size_t *offset);
 void fftwpp_conv_destroy(void *conv);
 /* out = {m,p,q,n,D,inplace,C,S} of dimension d */
 void fftwpp_conv_params(void *conv, int d, size_t *out);
