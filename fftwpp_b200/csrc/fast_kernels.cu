@@ -1138,8 +1138,11 @@ __device__ __forceinline__ double2 *loadTables(const PlanDev& P,
   return p;
 }
 
-template<int KIND, int LG, bool DIRECT>
-__global__ void __launch_bounds__(512)
+// NT: launch bound.  The staged/gathering variants need fewer registers than
+// the DIRECT ones, so their 256-thread configurations are compiled for three
+// CTAs per SM (24 warps instead of 16 to hide the load latency).
+template<int KIND, int LG, bool DIRECT, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1)
 fast_forward_many(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                   int layout, const void *f, void *F, long long nrows,
                   long long frs, long long Frs, int T, int ntc, size_t inbytes,
@@ -1553,6 +1556,18 @@ bool convPipeEnabled()
   return on == 1;
 }
 
+// FFTWPP_THREE_CTAS=0: compile-bound the gathering real forward pass for two
+// CTAs per SM instead of three (A/B switch)
+bool threeCtasEnabled()
+{
+  static int on=-1;
+  if(on < 0) {
+    const char *s=getenv("FFTWPP_THREE_CTAS");
+    on=(s && *s == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 bool fastDisabled()
 {
   static int off=-1;
@@ -1593,6 +1608,7 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g,
   const int M=1 << lg;
   g.mixed=fi->uniform ? 0 : 1;
   g.direct=fi->uniform && KIND == FFTWPP_KIND_COMPLEX && fi->nterm == 1;
+
   int twn=0;
   for(int k=0; k < lg/3; ++k)
     if(lg-3*(k+1) > 0) twn += 7 << (lg-3*(k+1));
@@ -1666,15 +1682,24 @@ int launchForwardMany(Plan *pl, int lg, uint64_t sb0, uint64_t nsb, int layout,
   dev.omPlane0=omPlane0;
   // zeta rows are indexed by sub-block slot within [sb0,sb0+nsb)
   int rc=0;
-#define CALLD(LGV, DIR)                                                      \
-  rc=allowSmem(fast_forward_many<KIND,LGV,DIR>);                             \
+#define CALLD(LGV, DIR, NTV)                                                 \
+  rc=allowSmem(fast_forward_many<KIND,LGV,DIR,NTV>);                         \
   if(rc) return rc;                                                          \
   prof_begin(4*pl->tag+0,st);                                                \
-  fast_forward_many<KIND,LGV,DIR><<<(unsigned) g.grid,g.nthreads,g.smem,st>>> \
+  fast_forward_many<KIND,LGV,DIR,NTV>                                        \
+    <<<(unsigned) g.grid,g.nthreads,g.smem,st>>>                             \
     (dev,pl->dsub+sb0,(int) nsb,layout,f,F,(long long) nrows,            \
      (long long) frs,(long long) Frs,g.T,g.ntc,g.tilebytes,g.zlen,g.mixed,   \
      (long long) g.ntiles,g.pair,g.ppStride);
-#define CALL(LGV) if(g.direct) {CALLD(LGV,true)} else {CALLD(LGV,false)}
+  // measured (512^3, B200): 3 CTAs/SM speeds the gathering real pass up by
+  // 15 %; bounding the DIRECT complex passes the same way (spills) or letting
+  // them re-gather their inputs per sub-block costs 35-40 %
+  const bool three=KIND == FFTWPP_KIND_REAL && !g.direct &&
+    g.nthreads <= 256 && g.tilebytes == 0 && threeCtasEnabled();
+#define CALL(LGV)                                                            \
+  if(g.direct) {CALLD(LGV,true,512)}                                         \
+  else if(KIND == FFTWPP_KIND_REAL && three) {CALLD(LGV,false,256)}          \
+  else {CALLD(LGV,false,512)}
   LG_CASES(CALL)
 #undef CALL
 #undef CALLD
