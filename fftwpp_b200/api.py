@@ -197,6 +197,22 @@ class HybridConv:
         lib.fftwpp_conv_convolve(self._h, ptrs, 1 if normalized else 0)
         return arrays[0] if self.B == 1 else arrays[:self.B]
 
+    def convolve_async(self, arrays, slot=0, normalized=True):
+        """Pipelined form of convolve() for PINNED host arrays (pinned_array):
+        returns at once; wait(slot) blocks until the outputs are back in
+        arrays[0:B].  Two slots: alternate them to overlap one convolution's
+        PCIe transfers with the other's compute."""
+        n = max(self.A, self.B)
+        ptrs = (ctypes.c_void_p * n)(*[_ptr(a) for a in arrays[:n]])
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[slot] = arrays  # keep the buffers alive until wait()
+        lib.fftwpp_conv_convolve_async(self._h, ptrs, 1 if normalized else 0, slot)
+
+    def wait(self, slot=0):
+        lib.fftwpp_conv_wait(self._h, slot)
+        if hasattr(self, "_inflight"):
+            self._inflight.pop(slot, None)
+
     def convolve_rows(self, arrays, nrows, rowstride, normalized=True):
         """1-D objects: nrows independent convolutions in one batched launch
         (device tensors shaped (nrows, rowstride))."""

@@ -64,11 +64,31 @@ struct Conv {
   size_t A,B;
   size_t doubles;
 
-  Conv() : dim(0), c1(NULL), c2(NULL), c3(NULL), A(0), B(0), doubles(0) {
+  // pipelined host-buffer entry: two slots of device staging, copy streams
+  // and events (see fftwpp_conv_convolve_async)
+  void *h2d,*d2h;
+  void *evIn[2],*evDone[2],*evOut[2];
+  bool busy[2];
+  DeviceArrays slotBuf[2];
+
+  Conv() : dim(0), c1(NULL), c2(NULL), c3(NULL), A(0), B(0), doubles(0),
+           h2d(NULL), d2h(NULL) {
     for(int d=0; d < 3; ++d) {app[d]=NULL; fft[d]=NULL;}
+    for(int s=0; s < 2; ++s) {
+      evIn[s]=evDone[s]=evOut[s]=NULL;
+      busy[s]=false;
+    }
   }
 
   ~Conv() {
+    for(int s=0; s < 2; ++s) {
+      if(busy[s]) fftwpp_gpu_event_sync(evOut[s]);
+      if(evIn[s]) fftwpp_gpu_event_destroy(evIn[s]);
+      if(evDone[s]) fftwpp_gpu_event_destroy(evDone[s]);
+      if(evOut[s]) fftwpp_gpu_event_destroy(evOut[s]);
+    }
+    if(h2d) fftwpp_gpu_stream_destroy(h2d);
+    if(d2h) fftwpp_gpu_stream_destroy(d2h);
     delete c1; delete c2; delete c3;
     for(int d=2; d >= 0; --d) {
       delete fft[d];
@@ -375,6 +395,53 @@ size_t fftwpp_conv_doubles(void *conv) {return ((Conv *) conv)->doubles;}
 void fftwpp_conv_convolve(void *conv, double **f, int normalized)
 {
   ((Conv *) conv)->convolve((Complex **) f,normalized != 0);
+}
+
+void fftwpp_conv_convolve_async(void *conv, double **f, int normalized,
+                                int slot)
+{
+  Conv *c=(Conv *) conv;
+  if(slot < 0 || slot > 1) {
+    std::cerr << "fftwpp_conv_convolve_async: slot must be 0 or 1" << std::endl;
+    exit(-1);
+  }
+  if(!c->h2d) {
+    gpu::check(fftwpp_gpu_stream_create(&c->h2d),"stream creation");
+    gpu::check(fftwpp_gpu_stream_create(&c->d2h),"stream creation");
+    for(int s=0; s < 2; ++s) {
+      gpu::check(fftwpp_gpu_event_create(&c->evIn[s]),"event creation");
+      gpu::check(fftwpp_gpu_event_create(&c->evDone[s]),"event creation");
+      gpu::check(fftwpp_gpu_event_create(&c->evOut[s]),"event creation");
+    }
+  }
+  size_t N=std::max(c->A,c->B);
+  size_t bytes=c->doubles*sizeof(double);
+  c->slotBuf[slot].ensure(N,bytes);
+  void *st=gpu::stream();
+  // the slot's staging buffers are free once its previous outputs have left
+  if(c->busy[slot])
+    gpu::check(fftwpp_gpu_stream_wait_event(c->h2d,c->evOut[slot]),"wait");
+  std::vector<Complex *> d(N);
+  for(size_t a=0; a < N; ++a) d[a]=(Complex *) c->slotBuf[slot].ptr[a];
+  for(size_t a=0; a < c->A; ++a)
+    gpu::check(fftwpp_gpu_memcpy_h2d(d[a],f[a],bytes,c->h2d),"h2d");
+  gpu::check(fftwpp_gpu_event_record(c->evIn[slot],c->h2d),"event");
+  gpu::check(fftwpp_gpu_stream_wait_event(st,c->evIn[slot]),"wait");
+  c->convolve(d.data(),normalized != 0);
+  gpu::check(fftwpp_gpu_event_record(c->evDone[slot],st),"event");
+  gpu::check(fftwpp_gpu_stream_wait_event(c->d2h,c->evDone[slot]),"wait");
+  for(size_t b=0; b < c->B; ++b)
+    gpu::check(fftwpp_gpu_memcpy_d2h(f[b],d[b],bytes,c->d2h),"d2h");
+  gpu::check(fftwpp_gpu_event_record(c->evOut[slot],c->d2h),"event");
+  c->busy[slot]=true;
+}
+
+void fftwpp_conv_wait(void *conv, int slot)
+{
+  Conv *c=(Conv *) conv;
+  if(slot < 0 || slot > 1 || !c->busy[slot]) return;
+  gpu::check(fftwpp_gpu_event_sync(c->evOut[slot]),"event sync");
+  c->busy[slot]=false;
 }
 
 void fftwpp_conv_convolve_rows(void *conv, double **f, size_t nrows,

@@ -159,6 +159,12 @@ int fftwpp_gpu_event_record(void *event, void *stream)
   return 0;
 }
 
+int fftwpp_gpu_event_sync(void *event)
+{
+  CUDA_TRY(cudaEventSynchronize((cudaEvent_t) event),"cudaEventSynchronize");
+  return 0;
+}
+
 int fftwpp_gpu_stream_wait_event(void *stream, void *event)
 {
   CUDA_TRY(cudaStreamWaitEvent((cudaStream_t) stream,(cudaEvent_t) event,0),

@@ -149,6 +149,15 @@ void fftwpp_conv_convolve(void *conv, double **f, int normalized);
  * (row i of array a at f[a]+i*rowstride words; device pointers).  This is what
  * Convolution2/3 issue for their innermost dimension and what the reference's
  * OpenMP loop over rows does (convolve.h:1434-1445); BASELINE config 5. */
+/* Pipelined host-buffer entry: enqueue the H2D copy of the inputs, the
+ * convolution and the D2H copy of the B outputs on three streams and return at
+ * once; fftwpp_conv_wait(slot) blocks until the outputs of that slot have
+ * landed in f[0..B).  Two slots (0, 1): while one convolution runs, the next
+ * one's inputs are already crossing PCIe and the previous one's outputs are on
+ * their way back.  f must be pinned host memory (fftwpp_gpu_malloc_host) that
+ * stays untouched until the wait. */
+void fftwpp_conv_convolve_async(void *conv, double **f, int normalized, int slot);
+void fftwpp_conv_wait(void *conv, int slot);
 void fftwpp_conv_convolve_rows(void *conv, double **f, size_t nrows,
                                size_t rowstride, int normalized);
 /* batch size (x rows) of the y/z sweep of a 3-D convolution; 0 = all rows */

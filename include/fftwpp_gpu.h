@@ -123,6 +123,7 @@ int fftwpp_gpu_event_create(void **event);
 int fftwpp_gpu_event_destroy(void *event);
 int fftwpp_gpu_event_record(void *event, void *stream);
 int fftwpp_gpu_stream_wait_event(void *stream, void *event);
+int fftwpp_gpu_event_sync(void *event);
 int fftwpp_gpu_device_sync(void);
 /* 1 if ptr is device (or managed) memory, 0 if host, <0 on error */
 int fftwpp_gpu_is_device_ptr(const void *ptr);

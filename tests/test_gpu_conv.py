@@ -287,3 +287,30 @@ def test_multnone_general_A_B(A, B):
     conv.convolve(arrays)
     for b in range(B):
         assert O.rel_l2(arrays[b], keep[b]) < 1e-12
+
+
+def test_async_pipeline_matches_blocking_call():
+    """convolve_async/wait (two slots, pinned host buffers) returns the same
+    results as the blocking call, step after step."""
+    L = (32, 16, 24)
+    rng = np.random.default_rng(77)
+    conv = fp.HybridConv(list(L), [2 * l for l in L], family=fp.FAMILY_REAL)
+    sets, wants = [], []
+    for step in range(5):
+        f, g = rng.uniform(-1, 1, L), rng.uniform(-1, 1, L)
+        wants.append(O.conv_real(f, g))
+        bufs = [fp.pinned_array(L, np.float64) for _ in range(2)]
+        bufs[0][...] = f
+        bufs[1][...] = g
+        sets.append(bufs)
+    for step in range(5):
+        s = step % 2
+        conv.wait(s)
+        if step >= 2:
+            assert O.rel_l2(sets[step - 2][0], wants[step - 2]) < 1e-12
+        conv.convolve_async(sets[step], slot=s)
+    conv.wait(0)
+    conv.wait(1)
+    for step in (3, 4):
+        assert O.rel_l2(sets[step][0], wants[step]) < 1e-12
+    conv.close()
