@@ -30,10 +30,9 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner
-# (printed to stdout at NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL prints its "NCCL version ..."
+# banner (and any NCCL_DEBUG output) to stdout unless told otherwise
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)

@@ -95,6 +95,7 @@ _sig("fftwpp_mpiconv3_convolve", None, c_void_p, P(c_void_p), c_int)
 _sig("fftwpp_mpiconv3_exchange_table", None, c_void_p, c_int, P(ctypes.c_ulonglong),
      P(ctypes.c_ulonglong), P(ctypes.c_ulonglong), P(ctypes.c_ulonglong))
 _sig("fftwpp_mpiconv3_set_plane_chunk", None, c_void_p, c_size_t)
+_sig("fftwpp_mpiconv3_symmetrize", None, c_void_p, c_void_p)
 _sig("fftwpp_mpiconv2_create", c_void_p, c_int, P(c_size_t), P(c_size_t), P(c_size_t),
      P(c_size_t), P(c_long), c_size_t, c_size_t, c_int, c_int, c_int, c_void_p)
 _sig("fftwpp_mpiconv2_destroy", None, c_void_p)

@@ -627,6 +627,16 @@ void fftwpp_mpiconv2_exchange_table(void *conv, int direction,
   fftwpp_mpiconv3_exchange_table(conv,direction,scount,sdispl,rcount,rdispl);
 }
 
+void fftwpp_mpiconv3_symmetrize(void *conv, double *f)
+{
+  MpiConv *c=(MpiConv *) conv;
+  if(!c->conv3) {
+    std::cerr << "fftwpp_mpiconv3_symmetrize needs a 3-D handle" << std::endl;
+    exit(-1);
+  }
+  c->conv3->HermitianSymmetrizeXY((Complex *) f);
+}
+
 void fftwpp_mpiconv3_set_plane_chunk(void *conv, size_t chunk)
 {
   MpiConv *c=(MpiConv *) conv;

@@ -396,6 +396,56 @@ void Convolution3MPI::runFused(Complex **f, size_t offset, double sc)
                                    f[b]+offset,0,sc,1,0,0,st),"backward");
 }
 
+void Convolution3MPI::HermitianSymmetrizeXY(Complex *f)
+{
+  if(!gpu::isDevice(f)) {
+    std::cerr << "distributed convolutions need device pointers" << std::endl;
+    exit(-1);
+  }
+  void *st=gpu::stream();
+  const int P=group.size;
+  const size_t Ly=d.Y, Z=d.Z, dy=d.y;
+  const size_t ymax=ceilquotient(Ly,(size_t) P);
+  const size_t n=Lx*ymax;
+  const size_t w=sizeof(Complex);
+  // z=0 entries of the local slab, padded to ymax rows of y per x
+  std::vector<Complex> mine(n,Complex(0.0,0.0)), all(n*P);
+  for(size_t i=0; i < Lx; ++i)
+    gpu::check(fftwpp_gpu_memcpy2d(&mine[i*ymax],w,f+i*dy*Z,Z*w,w,dy,1,st),
+               "d2h (z=0 plane)");
+  DeviceArrays tmp;
+  tmp.ensure(1,n*w*(P+1));
+  char *send=(char *) tmp.ptr[0];
+  char *recv=send+n*w;
+  gpu::check(fftwpp_gpu_memcpy_h2d(send,mine.data(),n*w,st),"h2d");
+  gpu::check(fftwpp_gpu_comm_allgather(group.comm,send,recv,n*w,st),
+             "all-gather (z=0 plane)");
+  gpu::check(fftwpp_gpu_memcpy_d2h(all.data(),recv,n*w*P,st),"d2h");
+  gpu::check(fftwpp_gpu_stream_sync(st),"sync");
+  std::vector<Complex> plane(Lx*Ly);
+  for(int p=0; p < P; ++p) {
+    size_t py0;
+    size_t py=localdimension(Ly,p,P,&py0);
+    for(size_t i=0; i < Lx; ++i)
+      for(size_t j=0; j < py; ++j)
+        plane[i*Ly+py0+j]=all[(size_t) p*n+i*ymax+j];
+  }
+  const size_t Hx=ceilquotient(Lx,2), Hy=ceilquotient(Ly,2);
+  fftwpp::HermitianSymmetrizeXY(Hx,Hy,1,Lx/2,Ly/2,plane.data(),Ly,1);
+  for(size_t i=0; i < Lx; ++i) {
+    for(size_t j=0; j < dy; ++j) mine[i*ymax+j]=plane[i*Ly+d.y0+j];
+    gpu::check(fftwpp_gpu_memcpy2d(f+i*dy*Z,Z*w,&mine[i*ymax],w,w,dy,0,st),
+               "h2d (z=0 plane)");
+  }
+  // even lengths carry an unpaired Nyquist row at index 0: zero it for every z
+  if(Lx/2 == Hx && dy > 0)
+    gpu::check(fftwpp_gpu_memset(f,0,dy*Z*w,st),"memset");
+  if(Ly/2 == Hy && d.y0 == 0 && dy > 0)
+    for(size_t i=0; i < Lx; ++i)
+      gpu::check(fftwpp_gpu_memset(f+i*dy*Z,0,Z*w,st),"memset");
+  gpu::check(fftwpp_gpu_stream_sync(st),"sync");
+}
+
 void Convolution3MPI::convolveRaw(Complex **f, size_t offset, Indices *)
 {
   if(fused) runFused(f,offset,1.0);

@@ -145,6 +145,14 @@ public:
   // env FFTWPP_MPI_FUSED=0 selects the NCCL all-to-all path.
   bool fused;
 
+  // Enforce Hermitian symmetry on the distributed centred data of a Hermitian
+  // run (fftx, ffty centred, fftz Hermitian): f is this rank's DEVICE slab
+  // Lx x d.y x d.Z.  Counterpart of the reference's
+  // HermitianSymmetrizeXY(split3&, Complex *), mpi/mpiconvolve.cc:11-142:
+  // only the z=0 plane carries a constraint, so the ranks all-gather that
+  // plane, apply the serial rule (convolve.h:1208-1267) and keep their slice.
+  void HermitianSymmetrizeXY(Complex *f);
+
 protected:
   bool fusedReady;
   std::vector<void *> peerT;   // [p*N+a]: peer p's transposed buffer a

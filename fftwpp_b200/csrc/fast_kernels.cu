@@ -613,20 +613,12 @@ fast_conv_rows_pipe(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
     long long nrow=ngrp*ROWS+rowInCta;
     if(nrow >= nrows) nrow=nrows-1;
     const double2 *n1=f1+nrow*rs;
-    { // pull the group after next into L2 ahead of its register loads
-      long long prow=(ngrp+gridDim.x)*ROWS+rowInCta;
-      if(prow < nrows) {
-        const char *p0=(const char *) (f0+prow*rs);
-        const char *p1=(const char *) (f1+prow*rs);
-        for(int off=tau*128; off < L*16; off += TPT*128) {
-          asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
-          asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
-        }
-      }
-      if(grp == blockIdx.x && more) { // first iteration: the next group too
-        const char *p0=(const char *) (f0+nrow*rs);
-        for(int off=tau*128; off < L*16; off += TPT*128)
-          asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
+    if(more) { // pull the next group's rows into L2 ahead of their register loads
+      const char *p0=(const char *) (f0+nrow*rs);
+      const char *p1=(const char *) n1;
+      for(int off=tau*128; off < L*16; off += TPT*128) {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
       }
     }
 

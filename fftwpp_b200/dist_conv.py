@@ -151,6 +151,12 @@ class SlabConvolution3:
     def set_plane_chunk(self, chunk):
         lib.fftwpp_mpiconv3_set_plane_chunk(self._h, int(chunk))
 
+    def symmetrize(self, array):
+        """Hermitian family: enforce the symmetry of the GLOBAL field on this
+        rank's device slab (collective; reference HermitianSymmetrizeXY(split3&))."""
+        lib.fftwpp_mpiconv3_symmetrize(self._h, ctypes.c_void_p(_ptr(array)))
+        return array
+
     def close(self):
         if self._h:
             lib.fftwpp_mpiconv3_destroy(self._h)

@@ -186,6 +186,10 @@ void fftwpp_mpiconv3_exchange_table(void *conv, int direction,
                                     unsigned long long *rcount,
                                     unsigned long long *rdispl);
 void fftwpp_mpiconv3_set_plane_chunk(void *conv, size_t chunk);
+/* family 1: enforce Hermitian symmetry on the distributed data (device slab
+ * Lx x y x ceil(Lz/2)); the reference's HermitianSymmetrizeXY(split3&, f),
+ * mpi/mpiconvolve.cc:11-142.  Collective over the communicator. */
+void fftwpp_mpiconv3_symmetrize(void *conv, double *f);
 
 /* ---- distributed 2-D convolution: the reference's Convolution2MPI
  * (mpi/mpiconvolve.h:72-179; driver mpi/tests/hybridconv2.cc).  Arrays are the

@@ -61,16 +61,26 @@ def main():
 
     # centred Hermitian 3-D (reference mpi/tests/hybridconvh3.cc): the global
     # field is symmetrised, every rank takes its y slice of the half-spectrum
-    for L in ((8, 2 * world + 2, 10), (12, 4 * world, 7)):
+    for L in ((8, 2 * world + 2, 10), (12, 4 * world, 7), (9, 2 * world + 1, 6)):
         M = [3 * l // 2 + 1 for l in L]
         c = dist_conv.SlabConvolution3(*L, *M, rank, world, family=fp.FAMILY_HERMITIAN,
                                        mult=fp.MULT_REALBINARY)
         H = (L[2] + 1) // 2
         full = [seeded((L[0], L[1], H), 17 + a, True) for a in range(2)]
+        y, y0 = c.split["y"], c.split["y0"]
+        # the distributed symmetrisation must equal the serial rule on the global field
+        f = [torch.from_numpy(np.ascontiguousarray(a[:, y0:y0 + y, :])).cuda() for a in full]
         for a in full:
             O.symmetrize(L, a)
-        y, y0 = c.split["y"], c.split["y0"]
-        f = [torch.from_numpy(np.ascontiguousarray(a[:, y0:y0 + y, :])).cuda() for a in full]
+        for a in range(2):
+            c.symmetrize(f[a])
+            same = np.array_equal(f[a].cpu().numpy(), full[a][:, y0:y0 + y, :])
+            t = torch.tensor([0.0 if same else 1.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print("distributed HermitianSymmetrizeXY L %s array %d:" % (L, a),
+                      "exact" if t.item() == 0 else "MISMATCH")
+            ok = ok and t.item() == 0
         want = O.conv_hermitian(L, full[0], full[1])
         c.convolve(f)
         torch.cuda.synchronize()
