@@ -30,9 +30,11 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: NCCL prints its "NCCL version ..."
-# banner (and any NCCL_DEBUG output) to stdout unless told otherwise
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line: at NCCL_DEBUG=VERSION (the GPU boxes'
+# default) NCCL prints a "NCCL version ..." banner to stdout; NCCL_DEBUG_FILE
+# does not redirect it, so drop that level (explicit WARN/INFO are respected)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
