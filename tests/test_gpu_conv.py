@@ -314,3 +314,24 @@ def test_async_pipeline_matches_blocking_call():
     for step in (3, 4):
         assert O.rel_l2(sets[step][0], wants[step]) < 1e-12
     conv.close()
+
+
+@pytest.mark.parametrize("L,M,mult", [(512, 1024, None), (400, 800, None), (512, 1536, None),
+                                      (300, 1024, fp.MULT_CORRELATION)])
+def test_conv_rows_m512_batches(L, M, mult):
+    """Batched rows on the m=512, p=1 fused row kernels (the z pass of cfg4):
+    ragged row counts, L < m, q = 2 and 3, both built-in multipliers."""
+    import torch
+    rng = np.random.default_rng(L + M)
+    conv = fp.HybridConv([L], [M], m=[512], D=[1], I=[0], mult=mult)
+    for rows in (1, 7, 19, 300):
+        f, g = crand(rng, rows, L), crand(rng, rows, L)
+        td = [torch.from_numpy(f.copy()).cuda(), torch.from_numpy(g.copy()).cuda()]
+        conv.convolve_rows(td, rows, L)
+        torch.cuda.synchronize()
+        got = td[0].cpu().numpy()
+        for i in (0, rows // 2, rows - 1):
+            want = (O.correlation_complex(f[i], g[i]) if mult == fp.MULT_CORRELATION
+                    else O.conv_complex(f[i], g[i]))
+            assert O.rel_l2(got[i], want) < 1e-12, (rows, i)
+    conv.close()
