@@ -49,6 +49,20 @@ def main():
     d = [torch.zeros(L, dtype=torch.complex128, device="cuda") for _ in range(2)]
     ms = timeit(lambda: c.convolve(d, normalized=False), 50)
     report("cfg1 1-D complex L=2^20 M=2^21", ms, 15 * L * 16, err, [c.params(0)])
+    # cfg1 is the reference's own CPU-runnable case: time it on the host cores
+    # beside the GPU number (oracle/_ref, its optimizer's choice, all threads)
+    try:
+        from oracle import ref as R
+        if R.available():
+            cores = min(int(R.lib().ref_get_max_threads()), os.cpu_count() or 1)
+            rc = R.RefConv([L], [2 * L], family=0, threads=cores)
+            t = sorted(rc.time(7)[2:])
+            print(json.dumps({"config": "cfg1 on the host CPU (reference, oracle/_ref)",
+                              "ms": 1e3 * t[len(t) // 2], "cores": cores,
+                              "params": [rc.params(0)]}))
+            rc.close()
+    except Exception as e:  # the CPU line is informative only
+        print(json.dumps({"config": "cfg1 on the host CPU", "error": repr(e)}))
 
     # cfg2: 2-D complex 4096^2
     n = 4096
@@ -109,6 +123,29 @@ def main():
     got = td[0].cpu().numpy()
     err = max(O.rel_l2(got[i], O.conv_complex(f[i], g[i])) for i in range(8))
     report("cfg5 4096 x 1-D complex L=8192", ms, 3 * rows * L * 16, err, [c.params(0)])
+    # batch sweep of the same rows
+    for nb in (1, 16, 256, 1024):
+        ms = timeit(lambda: c.convolve_rows(d, nb, L, normalized=False), 10)
+        print(json.dumps({"config": "cfg5 batch sweep", "rows": nb, "ms": ms,
+                          "rows_per_s": nb / (ms / 1e3)}))
+    del d, td
+    # cfg5 layout (ii): the same 4096 signals interleaved ("Many": C=S=4096) --
+    # forward of both inputs, multiply on the transformed data, backward; the
+    # fused kernels need contiguous rows, so this layout runs unfused
+    P = fp.Pad(0, L, 2 * L, rows, rows, 0, 0, -1, A=2, B=1)
+    f = torch.zeros((L, rows), dtype=torch.complex128, device="cuda")
+    F = torch.zeros(P.outputSize, dtype=torch.complex128, device="cuda")
+    calls = P.residue_calls()
+
+    def many_roundtrip():
+        for r in calls:
+            P.forward(f, r, F)
+            P.backward(F, f, r)
+    ms = timeit(many_roundtrip, 5)
+    print(json.dumps({"config": "cfg5 layout (ii): fftPad(8192,16384,C=S=4096) forward+backward, "
+                                "all residues", "ms": ms, "m": P.m, "p": P.p, "q": P.q, "D": P.D,
+                      "GBps": (1 + 2 * P.q) * rows * L * 16 / 1e9 / (ms / 1e3)}))
+    P.close()
 
 
 if __name__ == "__main__":
