@@ -437,7 +437,13 @@ void fftBase::choose(bool Explicit)
                  std::max(app.A,app.B)*mc*sizeof(Complex) :
                  Lin*word+mc*sizeof(Complex));
     bool inner=qc > 1 && innerEligible(kind(),L,mc,pc,C,S);
-    if(!mForced && !inner && lane > smemBytes) continue;
+    // the fused register kernels (fast_kernels.cu) hold a whole power-of-two
+    // row of up to 4096 points (2048 with two input terms) on chip
+    // regardless of the generic kernels' tile estimate
+    bool fusedRow=C == 1 && kind() == COMPLEX && app.A == 2 && app.B == 1 &&
+      (app.mult == multBinary || app.mult == multcorrelation) &&
+      ispow2(mc) && mc >= 16 && (pc == 1 ? mc <= 4096 : pc == 2 && mc <= 2048);
+    if(!mForced && !inner && !fusedRow && lane > smemBytes) continue;
     double N=(double) mc*qc;
     double cost;
     if(inner) { // two global passes + one fused pass
