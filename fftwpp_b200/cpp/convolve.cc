@@ -448,7 +448,10 @@ void fftBase::choose(bool Explicit)
     double cost;
     if(inner) { // two global passes + one fused pass
       double lm=log2((double) mc), lp=log2((double) pc);
-      cost=N*(lm+lp+8.0+0.25*fabs(lm-lp));
+      // measured on B200 (L=2^13 rows and L=2^20): flat optimum around
+      // m = 4p..8p (the fused stage prefers long rows, the strided stage
+      // short transforms)
+      cost=N*(lm+lp+8.0+0.25*fabs(lm-lp-2.5));
     } else {
       cost=N*(log2((double) mc)+2.0+pc)*(ispow2(mc) ? 1.0 : 2.5);
       if(pc > 2) cost *= 1.0+0.25*pc;
