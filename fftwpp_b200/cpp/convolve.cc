@@ -1076,9 +1076,6 @@ void Convolution::convolveRows(Complex **f, size_t offset, size_t nrows,
              "convolve");
 }
 
-// Unfused path for user-supplied host multipliers: forward every residue on
-// the GPU, run the multiplier on the host exactly as Convolution::operate does
-// (reference convolve.h:1120-1135), transform back on the GPU.
 // User multipliers are not fused: GPU forward of every residue -> multiplier
 // per residue block (reference operate(), convolve.h:1120-1135) -> GPU
 // backward.  With a registered device implementation the transformed data

@@ -54,6 +54,40 @@ def test_chooser_picks_valid_power_of_two_hybrid():
     assert (pad.p == 2 and pad.D == 2) or pad.q == 1
 
 
+def test_chooser_baseline_configs():
+    """The deterministic chooser's picks for the BASELINE configs (pinned so a
+    cost-model edit that changes the measured configurations is noticed)."""
+    def params(c, d):
+        p = c.params(d)
+        return p["m"], p["p"], p["q"]
+    c = fp.HybridConv([1 << 20], [1 << 21])                       # cfg1: two-stage inner
+    assert params(c, 0) == (2048, 512, 1024)
+    c = fp.HybridConv([4096, 4096], [8192, 8192])                 # cfg2: fused rows at m=4096
+    assert params(c, 0) == (4096, 1, 2) and params(c, 1) == (4096, 1, 2)
+    c = fp.HybridConv([256] * 3, [384] * 3, family=fp.FAMILY_HERMITIAN)   # cfg3
+    assert [params(c, d) for d in range(3)] == [(128, 2, 3)] * 3
+    c = fp.HybridConv([512] * 3, [1024] * 3, family=fp.FAMILY_REAL)       # cfg4 (headline)
+    assert [params(c, d) for d in range(3)] == [(512, 1, 2)] * 3
+    c = fp.HybridConv([8192], [16384])                            # cfg5: two-stage inner
+    assert params(c, 0) == (256, 32, 64)
+
+
+def test_device_multiplier_needs_host_function():
+    """fftwpp_conv_create_custom identifies the device multiplier by the host
+    function's address, so a NULL host function is refused."""
+    import subprocess
+    import sys
+    code = ("import ctypes, fftwpp_b200 as fp\n"
+            "from fftwpp_b200._lib import lib, HOST_MULT, DEVICE_MULT\n"
+            "a = (ctypes.c_size_t * 1)(8); b = (ctypes.c_size_t * 1)(16)\n"
+            "lib.fftwpp_conv_create_custom(1, 0, a, b, None, None, None, 0, 0, 2, 1,\n"
+            "    ctypes.cast(None, HOST_MULT), ctypes.cast(None, DEVICE_MULT))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       cwd=os.path.dirname(HERE))
+    assert r.returncode != 0
+    assert "host multiplier is required" in r.stderr
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device compute entry points must fail loudly."""
     import subprocess
