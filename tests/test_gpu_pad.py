@@ -66,6 +66,11 @@ def _input(kind, L, C, S, rng):
 
 @pytest.mark.parametrize("kind,L,M,m,C,S,D", cases())
 def test_forward_backward(kind, L, M, m, C, S, D):
+    check_pad(kind, L, M, m, C, S, D)
+
+
+def check_pad(kind, L, M, m, C, S, D):
+    """Forward Error / Backward Error of tests/hybrid.cc, hybridh.cc, hybridr.cc."""
     rng = np.random.default_rng(1234 + 7 * L + M + 13 * m)
     pad = fp.Pad(kind, L, M, C, S, m, D, 0, A=1, B=1)
     N = pad.paddedSize
