@@ -88,6 +88,24 @@ def test_device_multiplier_needs_host_function():
     assert "host multiplier is required" in r.stderr
 
 
+@pytest.mark.parametrize("args,needle", [
+    ((1, 9, 27, 1, 1, 3, 1, 0), "Invalid parameters"),     # centred with odd p
+    ((0, 8, 32, 1, 1, 8, 3, 0), "Invalid parameters"),     # odd D < n
+    ((3, 12, 24, 1, 1, 4, 1, 0), "Invalid parameters"),    # real: n even with odd p > 2
+    ((0, 16, 8, 1, 1, 0, 0, -1), "is greater than M"),     # L > M
+])
+def test_error_policy_matches_reference(args, needle):
+    """Errors are a message on stderr and exit(-1), never an exception or a
+    return code (reference convolve.h:226-232, convolve.cc:480-501)."""
+    import subprocess
+    import sys
+    code = "import fftwpp_b200 as fp\nfp.Pad(*%r)\nprint('constructed')\n" % (args,)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       cwd=os.path.dirname(HERE))
+    assert r.returncode != 0 and "constructed" not in r.stdout
+    assert needle in r.stderr
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device compute entry points must fail loudly."""
     import subprocess
