@@ -123,6 +123,30 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_cores():
+    """Cores this process may run on.  torchrun exports OMP_NUM_THREADS=1, which
+    omp_get_max_threads() would report; the CPU arm must use the whole box."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def reference_threads():
+    """Thread count for the reference CPU arm, forced into the OpenMP runtime."""
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)   # read by libgomp when it loads
+    from oracle import ref
+    lib = ref.lib()
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
+    lib.ref_set_maxthreads(cores)
+    return cores
+
+
 def reference_arm(args):
     """The reference's own CPU implementation (oracle/_ref), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -139,8 +163,7 @@ def reference_arm(args):
         out["unavailable"] = "oracle/_ref not built (reference needs FFTW3; shim build missing)"
         print(json.dumps(out))
         return
-    cores = int(ref.lib().ref_get_max_threads())
-    cores = min(cores, os.cpu_count() or cores)
+    cores = reference_threads()
     # (m,D,I) per dimension: the reference optimizer's own choice for this
     # geometry measured in the build container, forced here so the
     # timed run does not include its minutes-long timing search.
@@ -174,8 +197,7 @@ def cpu_baseline(L, budget_s=25.0):
         from oracle import ref
         if not ref.available():
             return None
-        cores = int(ref.lib().ref_get_max_threads())
-        cores = min(cores, os.cpu_count() or cores)
+        cores = reference_threads()
         m = [L, L // 2, L // 2]
         conv = ref.RefConv([L] * 3, [2 * L] * 3, family=2, m=m, D=[1, 1, 2], I=[0, 1, 1],
                            threads=cores)
@@ -196,6 +218,44 @@ def cpu_baseline(L, budget_s=25.0):
                 "sample": "failed: %r" % (e,)}
 
 
+def parity_pencils(f, g, points, workers):
+    """Checker (not timed, not shipped): z-pencils h[i,j,:] of the 3-D LINEAR
+    convolution h = f*g of two real arrays restricted to [0,L)^3, the quantity
+    tests/hybridconvr3.cc -E compares against (reference tests/direct.h:107-137
+    directconv3<double>), evaluated with partial FFTs: the z direction by a
+    zero-padded real FFT of every pencil, the x and y directions by the direct
+    double sum over i' <= i, j' <= j.  Cost O(L^3 log L + npoints L^3)."""
+    import scipy.fft as sfft
+    Lz = f.shape[2]
+    F = sfft.rfft(f, n=2 * Lz, axis=2, workers=workers)
+    G = sfft.rfft(g, n=2 * Lz, axis=2, workers=workers)
+    out = {}
+    for (i, j) in points:
+        H = np.einsum("abk,abk->k", F[:i + 1, :j + 1], G[i::-1, j::-1][:i + 1, :j + 1],
+                      optimize=False)
+        out[(i, j)] = sfft.irfft(H, n=2 * Lz)[:Lz]
+    return out
+
+
+def parity_points(L, y0, y):
+    """(i,j) pencils owned by the slab [y0,y0+y): corners, edges and interior."""
+    if y == 0:
+        return []
+    js = sorted(set([y0, y0 + y // 2, y0 + y - 1]))
+    is_ = sorted(set([0, 1 % L, L // 2 + 1 if L > 2 else 0, L - 1]))
+    return [(i, j) for i in is_ for j in js]
+
+
+def dist_conv_local(L, rank, world):
+    """(y0, y) of rank's slab: ceil split, last ranks short
+    (reference mpi/mpitranspose.h:118-130)."""
+    n = (L + world - 1) // world
+    s0 = n * rank
+    if s0 >= L:
+        return L, 0
+    return s0, (n if s0 + n <= L else L - s0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +266,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("FFTWPP_PLANE_CHUNK", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -250,6 +311,63 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- parity of THIS configuration, before anything is timed ----
+    # One normalised convolution of the seeded inputs; every rank compares
+    # z-pencils of its own slab with the partial-FFT linear convolution of the
+    # global fields (computed once, on rank 0).  Protocol of the reference's
+    # distributed test: mpi/tests/hybridconvr3.cc:132-167 (gather, serial
+    # convolution, checkerror max-norm, mpi/mpiutils.h:241-265).
+    parity = None
+    if not args.no_parity:
+        tol = 1e-12 * np.log2(float(2 * L) ** 3)
+        if world > 1:
+            full = runner.full_inputs(seed=1234)
+            y0, yl = runner.split["y0"], runner.split["y"]
+        else:
+            full = [a.cpu().numpy() for a in f]
+            y0, yl = 0, L
+        pts_all = [parity_points(L, *dist_conv_local(L, r, world)) for r in range(world)]
+        ref_vals = None
+        if rank == 0:
+            flat = sorted(set(p for pts in pts_all for p in pts))
+            ref_vals = parity_pencils(full[0], full[1], flat, host_cores())
+        if world > 1:
+            box = [ref_vals]
+            dist.broadcast_object_list(box, src=0)
+            ref_vals = box[0]
+        del full
+        fc = [a.clone() for a in f]
+        if world > 1:
+            runner.convolve(fc, normalized=True)
+        else:
+            conv.convolve(fc, normalized=True)
+        torch.cuda.synchronize()
+        mine = pts_all[rank]
+        num = den = mx = 0.0
+        for (i, j) in mine:
+            got = fc[0][i, j - y0, :].cpu().numpy()
+            want = ref_vals[(i, j)]
+            num += float(np.sum((got - want) ** 2))
+            den += float(np.sum(want ** 2))
+            mx = max(mx, float(np.max(np.abs(got - want))))
+        scale_ref = max(float(np.max(np.abs(v))) for v in ref_vals.values())
+        del fc
+        if world > 1:
+            t = torch.tensor([num, den], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            num, den = float(t[0].item()), float(t[1].item())
+            t = torch.tensor([mx], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mx = float(t.item())
+        rel = float(np.sqrt(num / den)) if den > 0 else float("nan")
+        parity = {"rel_l2": rel, "tol": tol, "ok": bool(rel <= tol),
+                  "max_abs_over_max_ref": mx / scale_ref if scale_ref > 0 else None,
+                  "pencils": sum(len(p) for p in pts_all), "ranks_checked": world,
+                  "against": "partial-FFT 3-D linear convolution of the same seeded global "
+                             "inputs (scipy rfft along z, direct sums over x and y; "
+                             "reference tests/direct.h:107-137), z-pencils at the corners, "
+                             "edges and interior of every rank's slab"}
 
     for _ in range(args.warmup):
         step()
@@ -396,8 +514,8 @@ def main():
         del hf
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(L)
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(L, budget_s=25.0 if world == 1 else 8.0)
 
     if rank == 0:
         out = {"metric": "hybrid_conv_per_s", "value": value, "unit": "conv/s",
@@ -413,7 +531,7 @@ def main():
                                 % (L ** 3 * 8 / 1e9)},
                "clocks": clocks, "gpu_launches": int(launches),
                "roofline": roofline, "roofline_conv": roofline_conv, "kernels": kernels,
-               "e2e": e2e, "cpu_baseline": cpu}
+               "e2e": e2e, "cpu_baseline": cpu, "parity": parity}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -19,66 +19,17 @@
 using namespace utils;
 
 namespace utils {
-
+// Must be a power of two and at least sizeof(Complex) (reference parallel.cc:18)
 size_t ALIGNMENT=2*sizeof(Complex);
-
-size_t ceilpow2(size_t n)
-{
-  size_t v=1;
-  while(v < n) v <<= 1;
-  return v;
 }
 
-static void *alignedBytes(size_t bytes)
-{
-  if(bytes == 0) return NULL;
-  void *p=NULL;
-  size_t al=std::max<size_t>(ALIGNMENT,sizeof(void *));
-  if(posix_memalign(&p,al,bytes) != 0) {
-    std::cerr << "Cannot allocate " << bytes << " bytes" << std::endl;
-    exit(1);
-  }
-  return p;
+// Host-thread globals of the reference's parallel.cc (:24,28,65-74).  The GPU
+// path does no host-threaded arithmetic, so there is no threshold to measure.
+size_t threshold=SIZE_MAX;
+namespace parallel {
+size_t lastThreads=SIZE_MAX;
+void Threshold(size_t threads) {lastThreads=threads;}
 }
-
-Complex *ComplexAlign(size_t size)
-{
-  return (Complex *) alignedBytes(size*sizeof(Complex));
-}
-
-Complex **ComplexAlign(size_t n, size_t size)
-{
-  if(n == 0 || size == 0) return NULL;
-  Complex **v=new Complex*[n];
-  size_t Size=ALIGNMENT*ceilquotient(size,ALIGNMENT);
-  Complex *B=ComplexAlign((n-1)*Size+size);
-  for(size_t i=0; i < n; ++i)
-    v[i]=B+i*Size;
-  return v;
-}
-
-double *doubleAlign(size_t size)
-{
-  return (double *) alignedBytes(size*sizeof(double));
-}
-
-double **doubleAlign(size_t n, size_t size)
-{
-  if(n == 0 || size == 0) return NULL;
-  double **v=new double*[n];
-  size_t Size=ALIGNMENT*ceilquotient(size,ALIGNMENT);
-  double *B=doubleAlign((n-1)*Size+size);
-  for(size_t i=0; i < n; ++i)
-    v[i]=B+i*Size;
-  return v;
-}
-
-void deleteAlign(void *p)
-{
-  free(p);
-}
-
-} // namespace utils
 
 namespace fftwpp {
 
@@ -154,7 +105,7 @@ void realMultBinary(Complex **F, size_t n, Indices *, size_t)
 void multcorrelation(Complex **F, size_t n, Indices *, size_t)
 {
   Complex *F0=F[0], *F1=F[1];
-  for(size_t j=0; j < n; ++j) F0[j] *= std::conj(F1[j]);
+  for(size_t j=0; j < n; ++j) F0[j] *= conj(F1[j]);
 }
 
 static int multiplierId(multiplier *mult)
@@ -1223,7 +1174,7 @@ void HermitianSymmetrizeX(size_t Hx, size_t Hy, size_t x0, Complex *f,
 {
   Complex *origin=f+x0*Sx;
   for(size_t i=1; i < Hx; ++i)
-    *(origin-i*Sx)=std::conj(origin[i*Sx]);
+    *(origin-i*Sx)=conj(origin[i*Sx]);
   origin[0]=Complex(origin[0].real(),0.0);
   if(x0 == Hx) // even length: zero the unpaired Nyquist row
     for(size_t j=0; j < Hy; ++j)
@@ -1237,12 +1188,12 @@ void HermitianSymmetrizeXY(size_t Hx, size_t Hy, size_t Hz, size_t x0,
   size_t origin=x0*Sx+y0*Sy;
   Complex *F=f+origin;
   for(size_t i=1; i < Hx; ++i)
-    *(F-i*Sx)=std::conj(F[i*Sx]);
+    *(F-i*Sx)=conj(F[i*Sx]);
   F[0]=Complex(F[0].real(),0.0);
 
   for(ptrdiff_t i=-(ptrdiff_t) Hx+1; i < (ptrdiff_t) Hx; ++i)
     for(size_t j=1; j < Hy; ++j)
-      f[origin-i*(ptrdiff_t) Sx-j*Sy]=std::conj(f[origin+i*(ptrdiff_t) Sx+j*Sy]);
+      f[origin-i*(ptrdiff_t) Sx-j*Sy]=conj(f[origin+i*(ptrdiff_t) Sx+j*Sy]);
 
   if(x0 == Hx) {
     size_t Ly=y0+Hy;

@@ -3,9 +3,11 @@
  *
  * Same class names, constructor signatures, public data members, size
  * queries and error behaviour ("message on cerr + exit", reference
- * convolve.h:226-232) as the reference, so existing callers (tests/hybrid*.cc,
- * examples/exampleconv*.cc, wrappers/cfftw++.cc) compile against it
- * unchanged.  What is different is everything underneath: the objects hold
+ * convolve.h:226-232) as the reference; together with the companion headers
+ * in this directory (Complex.h, fftw++.h, utils.h, align.h, parallel.h,
+ * seconds.h, statistics.h, Array.h) the reference's own callers
+ * (tests/hybrid*.cc, examples/exampleconv*.cc) compile against it unmodified
+ * and link with lib_fftwpp.so -- tests/refprogs/ builds and runs them.  What is different is everything underneath: the objects hold
  * GPU plans (include/fftwpp_gpu.h) instead of FFTW plans, there are no
  * per-routine forward1/forward2/forwardInner variants (one fused kernel family
  * covers them, see csrc/gpu_core.cu), and the residue loop of
@@ -22,41 +24,22 @@
 #ifndef FFTWPP_B200_CONVOLVE_H
 #define FFTWPP_B200_CONVOLVE_H
 
-#include <complex>
 #include <cstdint>
 #include <cstddef>
 #include <cstdlib>
 #include <iostream>
 #include <vector>
 
-#ifndef __Complex_h__
-typedef std::complex<double> Complex;
-#endif
+// The headers an existing caller gets through the reference's convolve.h
+// (reference convolve.h:22-25), so that `#include "convolve.h"` alone keeps
+// providing Complex, the aligned allocators, parallel::get_max_threads, the
+// timers and the Array classes.
+#include "Complex.h"
+#include "fftw++.h"
+#include "utils.h"
+#include "Array.h"
 
 struct fftwpp_gpu_plan;
-
-namespace utils {
-
-extern size_t ALIGNMENT; // bytes; reference parallel.cc:18
-
-inline size_t ceilquotient(size_t a, size_t b) {return (a+b-1)/b;}
-
-// Round n Complex words up to a multiple of ALIGNMENT bytes (align.h:155-158).
-inline size_t align(size_t n)
-{
-  return ceilquotient(n*sizeof(Complex),ALIGNMENT)*ALIGNMENT/sizeof(Complex);
-}
-
-size_t ceilpow2(size_t n);
-
-// Host allocators with the reference's names (align.h:109-171).
-Complex *ComplexAlign(size_t size);
-Complex **ComplexAlign(size_t n, size_t size);
-double *doubleAlign(size_t size);
-double **doubleAlign(size_t n, size_t size);
-void deleteAlign(void *p);
-
-} // namespace utils
 
 namespace fftwpp {
 
@@ -68,26 +51,6 @@ const Complex I(0.0,1.0);
 
 // Smallest 2^a 3^b 5^c 7^d >= m (reference convolve.cc:114-124).
 size_t nextfftsize(size_t m);
-
-// Thread bookkeeping kept for source compatibility (fftw++.h:59-80); the GPU
-// path does not use host threads.
-class ThreadBase {
-public:
-  size_t threads;
-  size_t innerthreads;
-  ThreadBase() : threads(1), innerthreads(1) {}
-  ThreadBase(size_t threads) : threads(threads), innerthreads(1) {}
-  void Threads(size_t nthreads) {threads=nthreads;}
-  size_t Threads() {return threads;}
-  size_t Innerthreads() {return innerthreads;}
-};
-
-// Placeholder for the reference's fftw base class statics (fftw++.cc:14,17).
-class fftw {
-public:
-  static size_t maxthreads;
-  static size_t effort;
-};
 
 class fftBase;
 

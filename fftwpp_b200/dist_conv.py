@@ -119,12 +119,12 @@ class SlabConvolution3:
     def local_shape(self):
         return (self.L[0], self.split["y"], self.L[2])
 
-    def make_inputs(self, seed=1234, scale_second=None):
-        """Seeded inputs: the local slab of a globally defined random field."""
+    def full_inputs(self, seed=1234, scale_second=None):
+        """The globally defined seeded fields (host numpy arrays, every rank
+        generates the same ones); make_inputs() takes this rank's slab."""
         import numpy as np
         import torch
         Lx, Ly, Lz = self.L
-        y, y0 = self.split["y"], self.split["y0"]
         out = []
         for a in range(self.A):
             g = torch.Generator(device="cpu").manual_seed(seed + a)
@@ -136,8 +136,15 @@ class SlabConvolution3:
                 g2 = torch.Generator(device="cpu").manual_seed(seed + 100 + a)
                 im = torch.rand((Lx, Ly, Lz), dtype=torch.float64, generator=g2) * 2 - 1
                 full = torch.complex(full, im * (full.abs().max()))
-            out.append(full[:, y0:y0 + y, :].contiguous().cuda())
+            out.append(full.numpy())
         return out
+
+    def make_inputs(self, seed=1234, scale_second=None):
+        """Seeded inputs: the local slab of a globally defined random field."""
+        import torch
+        y, y0 = self.split["y"], self.split["y0"]
+        return [torch.from_numpy(a[:, y0:y0 + y, :].copy()).cuda()
+                for a in self.full_inputs(seed, scale_second)]
 
     def convolve(self, arrays, normalized=True):
         n = max(self.A, self.B)

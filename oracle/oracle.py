@@ -171,14 +171,50 @@ def real_spectrum_at(F2, N, i):
 # convolutions (definitions: tests/direct.h, tests/direct.cc)
 # --------------------------------------------------------------------------
 
+class _FFT:
+    """numpy.fft, or scipy.fft (the same pocketfft algorithms, float64) run on
+    all host cores when scipy is importable -- only the wall time of the
+    full-size checks differs."""
+
+    def __init__(self):
+        try:
+            import scipy.fft as sf
+            try:
+                w = max(1, len(os.sched_getaffinity(0)))
+            except AttributeError:
+                w = os.cpu_count() or 1
+            self.kw = {"workers": w}
+            self.m = sf
+        except ImportError:
+            self.kw = {}
+            self.m = np.fft
+
+    def fftn(self, a, s=None, axes=None):
+        return self.m.fftn(a, s, axes=axes, **self.kw)
+
+    def ifftn(self, a, s=None, axes=None):
+        return self.m.ifftn(a, s, axes=axes, **self.kw)
+
+    def rfftn(self, a, s=None, axes=None):
+        return self.m.rfftn(a, s, axes=axes, **self.kw)
+
+    def irfftn(self, a, s=None, axes=None):
+        return self.m.irfftn(a, s, axes=axes, **self.kw)
+
+
+_fft = _FFT()
+
+
 def conv_complex(f, g):
     """h_i = sum_{j<=i} f_j g_{i-j} in every dimension (direct.h:19-26,77-88,
-    122-136), evaluated with explicitly zero-padded numpy FFTs."""
+    122-136), evaluated with explicitly zero-padded FFTs."""
     f = np.asarray(f, dtype=np.complex128)
     g = np.asarray(g, dtype=np.complex128)
     shape = [2 * n - 1 for n in f.shape]
     ax = list(range(f.ndim))
-    h = np.fft.ifftn(np.fft.fftn(f, shape, axes=ax) * np.fft.fftn(g, shape, axes=ax), axes=ax)
+    F = _fft.fftn(f, shape, axes=ax)
+    F *= _fft.fftn(g, shape, axes=ax)
+    h = _fft.ifftn(F, axes=ax)
     return np.ascontiguousarray(h[tuple(slice(0, n) for n in f.shape)])
 
 
@@ -198,15 +234,34 @@ def conv_real(f, g):
     g = np.asarray(g, dtype=np.float64)
     shape = [2 * n - 1 for n in f.shape]
     ax = list(range(f.ndim))
-    h = np.fft.irfftn(np.fft.rfftn(f, shape, axes=ax) * np.fft.rfftn(g, shape, axes=ax),
-                      shape, axes=ax)
+    F = _fft.rfftn(f, shape, axes=ax)
+    F *= _fft.rfftn(g, shape, axes=ax)
+    h = _fft.irfftn(F, shape, axes=ax)
     return np.ascontiguousarray(h[tuple(slice(0, n) for n in f.shape)])
+
+
+def conv_real_pencils(f, g, points):
+    """z-pencils h[i,j,:] of the 3-D real linear convolution (direct.h:107-137)
+    for the given (i,j): FFT along z only, direct sums over i' <= i, j' <= j.
+    Lets a 512^3 result be checked in seconds without the full 3-D oracle."""
+    f = np.asarray(f, dtype=np.float64)
+    g = np.asarray(g, dtype=np.float64)
+    Lz = f.shape[2]
+    F = _fft.m.rfft(f, n=2 * Lz, axis=2, **_fft.kw)
+    G = _fft.m.rfft(g, n=2 * Lz, axis=2, **_fft.kw)
+    out = {}
+    for (i, j) in points:
+        H = np.einsum("abk,abk->k", F[:i + 1, :j + 1], G[i::-1, j::-1][:i + 1, :j + 1])
+        out[(i, j)] = _fft.m.irfft(H, n=2 * Lz)[:Lz]
+    return out
 
 
 def _full_conv(a, b):
     shape = [x + y - 1 for x, y in zip(a.shape, b.shape)]
     ax = list(range(a.ndim))
-    return np.fft.ifftn(np.fft.fftn(a, shape, axes=ax) * np.fft.fftn(b, shape, axes=ax), axes=ax)
+    A = _fft.fftn(a, shape, axes=ax)
+    A *= _fft.fftn(b, shape, axes=ax)
+    return _fft.ifftn(A, axes=ax)
 
 
 def conv_centered1(f, g):

@@ -1,0 +1,45 @@
+"""Source compatibility of the C++ boundary: the reference's own
+callers -- examples/exampleconv*.cc, tests/hybrid*.cc with tests/options.cc and
+tests/direct.cc, wrappers/cexample.c -- compile UNMODIFIED against
+fftwpp_b200/cpp/*.h and link with lib_fftwpp.so (tests/refprogs/Makefile).
+CPU-side check: needs the reference sources, so it is skipped where
+/root/reference is absent (the GPU box runs the prebuilt binaries instead,
+tests/test_gpu_refprogs.py)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIR = os.path.join(ROOT, "tests", "refprogs")
+PROGS = ["exampleconv", "exampleconv2", "exampleconv3", "exampleconvh", "exampleconvh2",
+         "exampleconvh3", "exampleconvr", "exampleconvr2", "exampleconvr3", "cexample",
+         "hybridconv", "hybridconv2", "hybridconv3", "hybridconvh", "hybridconvh2",
+         "hybridconvh3", "hybridconvr", "hybridconvr2", "hybridconvr3", "hybrid", "hybridh",
+         "hybridr"]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/convolve.h"),
+                    reason="reference sources not present on this host")
+def test_reference_callers_compile_unmodified():
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    r = subprocess.run(["make", "-j8", "-C", DIR], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for p in PROGS:
+        assert os.access(os.path.join(DIR, "_build", p), os.X_OK), p
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(DIR, "_build", "hybridconv")),
+                    reason="tests/refprogs/_build not built")
+def test_reference_caller_fails_loudly_without_gpu():
+    """No CPU fallback: on a host without a CUDA device the unmodified
+    reference driver must exit non-zero with the library's message."""
+    import fftwpp_b200 as fp
+    if fp.lib.fftwpp_gpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([os.path.join(DIR, "_build", "hybridconv"), "-L8", "-M16", "-E", "-T1"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "fftwpp-b200:" in r.stderr  # the library's own error line (cerr + exit)
