@@ -110,6 +110,9 @@ _sig("fftwpp_conv_create_custom", c_void_p, c_int, c_int, P(c_size_t), P(c_size_
      P(c_size_t), P(c_size_t), P(c_long), c_size_t, c_size_t, c_size_t, c_size_t,
      HOST_MULT, DEVICE_MULT)
 _sig("fftwpp_indices_get", None, c_void_p, P(c_size_t), P(c_size_t))
+_sig("fftwpp_indices_size", c_size_t, c_void_p)
+_sig("fftwpp_indices_outer", c_size_t, c_void_p, c_size_t)
+_sig("fftwpp_indices_index", c_size_t, c_void_p, c_size_t)
 _sig("fftwpp_conv_convolve_async", None, c_void_p, P(c_void_p), c_int, c_int)
 _sig("fftwpp_conv_wait", None, c_void_p, c_int)
 _sig("fftwpp_conv_convolve_rows", None, c_void_p, P(c_void_p), c_size_t, c_size_t, c_int)

@@ -112,14 +112,16 @@ class HybridConv:
     """
 
     def __init__(self, L, M=None, family=FAMILY_COMPLEX, m=None, D=None, I=None,
-                 Sx=0, Sy=0, A=2, B=1, mult=None, device_mult=None):
+                 Sx=0, Sy=0, A=2, B=1, mult=None, device_mult=None, indexed=False):
         """mult: one of the MULT_* built-ins (fused on the GPU), or a Python
         callable mult(F, n, r, offset) -- the reference's user `multiplier`
         (convolve.h:78-82): F is a list of max(A,B) numpy views of the n
         transformed words of one residue block, results go to F[0:B].
         device_mult (with a callable mult): device_mult(ptrs, n, r, offset,
         stream) receives the DEVICE addresses of the same blocks and must only
-        enqueue GPU work; the transformed data then stays on the GPU."""
+        enqueue GPU work; the transformed data then stays on the GPU.
+        indexed=True: the callables receive (F, n, ctx[, stream]) where ctx
+        carries the whole transformed multi-index (ctx.outer, ctx.index(j))."""
         L = [int(v) for v in (L if hasattr(L, "__len__") else [L])]
         dim = len(L)
         if M is None:
@@ -137,7 +139,7 @@ class HybridConv:
         I = larr(*([-1] * dim if I is None else [int(v) for v in I]))
         self.dim, self.family, self.L, self.M, self.A, self.B = dim, family, L, M, A, B
         if callable(mult):
-            self._cb = self._callbacks(mult, device_mult, family, max(A, B))
+            self._cb = self._callbacks(mult, device_mult, family, max(A, B), indexed)
             self._h = lib.fftwpp_conv_create_custom(dim, family, arr(*L), arr(*M), m, D, I,
                                                     Sx, Sy, A, B, *self._cb)
         else:
@@ -146,25 +148,47 @@ class HybridConv:
         self.doubles = int(lib.fftwpp_conv_doubles(self._h))
 
     @staticmethod
-    def _callbacks(mult, device_mult, family, narrays):
+    def _callbacks(mult, device_mult, family, narrays, indexed=False):
         """ctypes thunks for a Python multiplier pair (kept alive by the object)."""
         import numpy as np
         from ._lib import HOST_MULT, DEVICE_MULT
         dtype = np.float64 if family == FAMILY_HERMITIAN else np.complex128
 
+        class Context(tuple):
+            """(r, offset) as before, plus the transformed multi-index of the
+            reference's `Indices` (convolve.h:48-76): .outer = indices->index[]
+            (outermost dimension last), .index(j) = fft->index(r, j+offset)."""
+            outer = ()
+            _ind = None
+
+            def index(self, j):
+                return int(lib.fftwpp_indices_index(self._ind, j))
+
         def context(indices):
             r, off = ctypes.c_size_t(), ctypes.c_size_t()
             lib.fftwpp_indices_get(indices, ctypes.byref(r), ctypes.byref(off))
-            return int(r.value), int(off.value)
+            c = Context((int(r.value), int(off.value)))
+            n = int(lib.fftwpp_indices_size(indices))
+            c.outer = tuple(int(lib.fftwpp_indices_outer(indices, d)) for d in range(n))
+            c._ind = indices
+            return c
 
         def host(F, n, indices, threads):
             views = [np.ctypeslib.as_array(ctypes.cast(F[a], ctypes.POINTER(ctypes.c_double)),
                                            shape=(n * (dtype().itemsize // 8),)).view(dtype)
                      for a in range(narrays)]
-            mult(views, n, *context(indices))
+            ctx = context(indices)
+            if indexed:
+                mult(views, n, ctx)
+            else:
+                mult(views, n, *ctx)
 
         def device(F, n, indices, stream):
-            device_mult([int(F[a]) for a in range(narrays)], n, *context(indices), stream)
+            ctx = context(indices)
+            if indexed:
+                device_mult([int(F[a]) for a in range(narrays)], n, ctx, stream)
+            else:
+                device_mult([int(F[a]) for a in range(narrays)], n, *ctx, stream)
 
         return (HOST_MULT(host),
                 DEVICE_MULT(device) if device_mult else ctypes.cast(None, DEVICE_MULT))

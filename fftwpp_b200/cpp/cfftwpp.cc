@@ -381,6 +381,23 @@ void fftwpp_indices_get(void *indices, size_t *r, size_t *offset)
   if(offset) *offset=i->offset;
 }
 
+size_t fftwpp_indices_size(void *indices)
+{
+  return ((Indices *) indices)->size;
+}
+
+size_t fftwpp_indices_outer(void *indices, size_t d)
+{
+  Indices *i=(Indices *) indices;
+  return d < i->size ? i->index[d] : 0;
+}
+
+size_t fftwpp_indices_index(void *indices, size_t j)
+{
+  Indices *i=(Indices *) indices;
+  return i->fft->index(i->r,j+i->offset);
+}
+
 void fftwpp_conv_destroy(void *conv) {delete (Conv *) conv;}
 
 void fftwpp_conv_params(void *conv, int d, size_t *out)
@@ -515,11 +532,16 @@ MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
   // dimension, so the slices are taken over its stored modes
   size_t y0;
   size_t y=utils::localdimension(len[1],rank,size,&y0);
-  if(y == 0) {
-    std::cerr << "rank " << rank << " has an empty y slab (more ranks than "
-              << "ceil-split rows); reduce the number of ranks" << std::endl;
-    exit(-1);
-  }
+  // Ranks beyond the ceil-split own no y rows (reference localdimension,
+  // mpi/mpitranspose.h:118-130, e.g. Ly=9 on 4 ranks: 3,3,3,0).  They still
+  // own transformed x rows and take part in both exchanges; their local x
+  // passes are skipped.  The plan of the (unused) x pass is built for one row.
+  size_t yPlan=std::max<size_t>(y,1);
+  // Every rank must run the x pass with the same (m,D,I): the reference picks
+  // them on rank 0 and broadcasts (mpi/tests/hybridconvr3.cc:87-102); here the
+  // deterministic chooser is evaluated for rank 0's slab width on every rank.
+  size_t mx=m[0], Dx=D[0];
+  long Ix=I[0];
   if(dim == 2 && family == 1) {
     std::cerr << "distributed 2-D Hermitian convolutions are not supported "
               << "(the Hermitian dimension cannot be the split one)"
@@ -534,13 +556,22 @@ MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
     else
       c->app[d]=new Application(A,B,mu,*c->app[d-1],m[d],D[d],Id);
   }
+  size_t rowWords=dim == 2 ? 1 : len[2];
+  if(mx == 0) {
+    size_t C0=utils::localdimension(len[1],0,size,NULL)*rowWords;
+    fftBase *probe=makePad(kinds[0],L[0],M[0],*c->app[0],C0,C0,0,0,-1);
+    mx=probe->m;
+    Dx=probe->D;
+    Ix=probe->inplace;
+    delete probe;
+  }
   if(dim == 2) {
-    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],y,y,m[0],D[0],I[0]);
+    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],yPlan,yPlan,mx,Dx,Ix);
     c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],1,0,m[1],D[1],I[1]);
     c->conv2=new Convolution2MPI(c->fft[0],c->fft[1],group);
   } else {
-    size_t Cx=y*len[2];
-    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],Cx,Cx,m[0],D[0],I[0]);
+    size_t Cx=yPlan*len[2];
+    c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],Cx,Cx,mx,Dx,Ix);
     c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],len[2],len[2],m[1],D[1],
                       I[1]);
     c->fft[2]=makePad(kinds[2],L[2],M[2],*c->app[2],1,0,m[2],D[2],I[2]);

@@ -108,6 +108,9 @@ void multcorrelation(Complex **F, size_t n, Indices *, size_t)
   for(size_t j=0; j < n; ++j) F0[j] *= conj(F1[j]);
 }
 
+// max(A,B) the fused convolution kernels accept (MAXARRAYS of the CUDA layer)
+static const size_t MAXFUSED=8;
+
 static int multiplierId(multiplier *mult)
 {
   if(mult == multNone) return FFTWPP_MULT_NONE;
@@ -152,6 +155,7 @@ void Indices::copy(Indices *indices, size_t size0)
     if(maxsize > 0) delete [] index;
     index=new size_t[size];
     maxsize=size;
+    for(size_t d=0; d < size; ++d) index[d]=0;
   }
   if(indices)
     for(size_t d=1; d < size; ++d)
@@ -197,6 +201,7 @@ fftBase::fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
   gpuplan(NULL), gputag(0), subHost(NULL), totalRows(0), devIn(NULL), devOut(NULL),
   twoStage(false), planA(NULL), planB(NULL)
 {
+  forcedCtor=false;
   checkParameters();
 }
 
@@ -210,6 +215,8 @@ fftBase::fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
 {
   checkParameters();
   this->app.D=D;
+  forcedCtor=true; // no optimizer scan => no parameter report (reference
+                   // convolve.cc:451-469 prints from OptBase::scan only)
 }
 
 fftBase::~fftBase()
@@ -318,7 +325,7 @@ const ResidueCall& fftBase::call(size_t r)
 
 void fftBase::report(const char *name)
 {
-  if(!app.verbose) return;
+  if(!app.verbose || forcedCtor) return;
   size_t mpL=m*p-L;
   std::cout << std::endl << "Optimal padding: ";
   if(p == q) std::cout << "Explicit" << std::endl;
@@ -383,7 +390,10 @@ void fftBase::choose(bool Explicit)
     if(mc*qc < (Explicit ? mc : M)) continue;
     size_t Dc=DForced ? app.D : (kind() == HERMITIAN && qc > 1 ? 2 : 1);
     if(!valid(mc,pc,qc,nc,Dc,kind() == HERMITIAN ? C : S)) continue;
-    if(qc > 1 && pc > 2 && (kind() == HERMITIAN || kind() == REAL)) continue;
+    // the chooser does not pick the inner (p > 2) layouts of the Hermitian
+    // and real classes on its own; forced values (Application.m) reach them
+    if(!mForced && qc > 1 && pc > 2 && (kind() == HERMITIAN || kind() == REAL))
+      continue;
     size_t lane=(C == 1 ? (app.A+app.B)*Lin*word+
                  std::max(app.A,app.B)*mc*sizeof(Complex) :
                  Lin*word+mc*sizeof(Complex));
@@ -980,9 +990,16 @@ Convolution::Convolution(fftBase *fft, Complex **, Complex *, Complex *) :
 {
   indices.copy(NULL,0);
   indices.fft=fft;
+  rowIndexDims=0;
   scale=1.0/normalization();
   if(fft->tag() == 0) fft->setTag(1);
   multId=multiplierId(mult);
+  if(std::max(A,B) > MAXFUSED && multId >= 0) {
+    // the fused kernels take at most MAXFUSED arrays; larger A or B run the
+    // unfused forward / multiply / backward path (the built-ins have host
+    // bodies, so they can serve as "user" multipliers there)
+    multId=-1;
+  }
   if(fft->C != 1 && multId != FFTWPP_MULT_NONE) {
     // as in the reference the multiplier only sees C == 1 data
   }
@@ -998,7 +1015,30 @@ void Convolution::convolveRows(Complex **f, size_t offset, size_t nrows,
     return;
   }
   size_t N=std::max(A,B);
-  void *ptrs[16];
+  void *ptrs[MAXFUSED];
+  if(fft->C != 1 && multId == FFTWPP_MULT_NONE) {
+    // C interleaved columns without a multiplier (what fft->report()/time()
+    // and tests/hybrid*.cc -C run): forward and backward passes over all
+    // residues; the fused row kernels need C == 1
+    const std::vector<ResidueCall>& calls=fft->calls();
+    size_t nsub=calls.back().sb0+calls.back().nsb;
+    bool herm=fft->kind() == fftBase::HERMITIAN;
+    size_t words=fft->allSize();
+    size_t wbytes=herm ? sizeof(double) : sizeof(Complex);
+    devT.ensure(1,nrows*words*wbytes);
+    size_t inWord=fft->wordSize() == 1 ? 1 : 1; // rowstride is in input words
+    (void) inWord;
+    void *st=gpu::stream();
+    for(size_t b=0; b < B; ++b) {
+      gpu::check(fftwpp_gpu_forward(fft->plan(),0,nsub,1,f[b]+offset,
+                                    devT.ptr[0],nrows,rowstride,words,st),
+                 "forward");
+      gpu::check(fftwpp_gpu_backward(fft->plan(),0,nsub,1,devT.ptr[0],
+                                     f[b]+offset,0,sc,nrows,words,rowstride,
+                                     st),"backward");
+    }
+    return;
+  }
   if(fft->innerFast() && multId != FFTWPP_MULT_NONE) {
     // two-stage large transform: f -> T (stage A), q rows of length m fused
     // in T (stage B), T -> f (stage A adjoint, normalisation folded in)
@@ -1080,6 +1120,11 @@ void Convolution::runCustom(Complex **f, size_t offset, size_t nrows,
         }
         indices.r=c.r;
         indices.offset=d*fft->b;
+        // outer transformed indices of this batched row (reference
+        // convolve.h:1442,1759 set them per row before the inner call)
+        if(rowIndexDims && (row+1)*rowIndexDims <= rowIndex.size())
+          for(size_t q=0; q < rowIndexDims && q < indices.maxsize; ++q)
+            indices.index[q]=rowIndex[row*rowIndexDims+q];
         if(dmult) (*dmult)(G.data(),rowsHere,&indices,st);
         else (*mult)(G.data(),rowsHere,&indices,threads);
         done += rowsHere;
@@ -1276,6 +1321,27 @@ void Convolution2::convolvePlanes(Complex **F, size_t offset, size_t nplanes,
       gpu::check(fftwpp_gpu_forward(fftx->plan(),0,nsub,1,src,devF.ptr[a],np,
                                     planestride,wordsPerPlane,st),"forward");
     }
+    if(convolvey[0]->customMultiplier()) {
+      // per batched row: index[0] = transformed index of this object's
+      // strided dimension, index[1] = the caller's (plane) index
+      bool outer=planeIndex.size() >= i0+np;
+      size_t dims=outer ? 2 : 1;
+      std::vector<size_t> table(np*rows*dims);
+      size_t base=indexBase();
+      for(size_t ic=0; ic < calls.size(); ++ic) {
+        const ResidueCall& c=calls[ic];
+        for(size_t k=0; k < c.rows; ++k) {
+          size_t idx=fftx->index(c.r,k+base);
+          for(size_t pl=0; pl < np; ++pl) {
+            size_t row=pl*rows+c.row0+k;
+            table[row*dims]=idx;
+            if(outer) table[row*dims+1]=planeIndex[i0+pl];
+          }
+        }
+      }
+      convolvey[0]->indices.copy(NULL,dims);
+      convolvey[0]->setRowIndices(table,dims);
+    }
     convolvey[0]->convolveRows(G.data(),0,np*rows,fftx->S,1.0);
     for(size_t bq=0; bq < B; ++bq) {
       if(bq < outBase.size() && outBase[bq]) {
@@ -1416,6 +1482,14 @@ void Convolution3::run(Complex **f, size_t offset, double sc)
     gpu::check(fftwpp_gpu_forward(fftx->plan(),0,nsub,1,d[a],devF.ptr[a],nr,
                                   rs,rs,st),"forward");
   // every transformed x row is an independent y-z convolution
+  if(convolveyz[0]->convolvey[0]->customMultiplier()) {
+    std::vector<size_t>& pi=convolveyz[0]->planeIndex;
+    pi.assign(rows,0);
+    size_t base=indexBase();
+    for(size_t ic=0; ic < calls.size(); ++ic)
+      for(size_t k=0; k < calls[ic].rows; ++k)
+        pi[calls[ic].row0+k]=fftx->index(calls[ic].r,k+base);
+  }
   convolveyz[0]->convolvePlanes(G.data(),0,rows,Sx,1.0);
   for(size_t bq=0; bq < B; ++bq)
     gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[bq],d[bq],

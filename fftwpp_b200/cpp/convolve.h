@@ -245,6 +245,7 @@ protected:
   size_t totalRows;
   void *devIn,*devOut; // staging for host-pointer forward()/backward()
   bool twoStage;
+  bool forcedCtor; // built by a forced (m,D,I) constructor
   fftwpp_gpu_plan *planA,*planB;
 
   fftBase(size_t L, size_t M, Application& app, size_t C, size_t S,
@@ -407,8 +408,19 @@ public:
   void convolveRows(Complex **f, size_t offset, size_t nrows,
                     size_t rowstride, double scale);
 
+  // Transformed outer indices of the rows of the next convolveRows() batch,
+  // `dims` entries per row (row-major): what the reference's per-row loops
+  // store in indices.index[d] before each inner convolveRaw
+  // (reference convolve.h:1442,1759).  Only consulted for user multipliers.
+  void setRowIndices(const std::vector<size_t>& table, size_t dims) {
+    rowIndex=table; rowIndexDims=dims;
+  }
+  bool customMultiplier() const {return multId < 0;}
+
 protected:
   int multId;
+  std::vector<size_t> rowIndex;
+  size_t rowIndexDims;
   DeviceArrays dev;
   DeviceArrays devT; // stage-A output of two-stage transforms
   void run(Complex **f, size_t offset, double scale);
@@ -485,6 +497,11 @@ public:
   // of back into F[b] (device arrays; see fftwpp_gpu_backward_mapped).
   std::vector<const uint64_t *> outBase;
   std::vector<const int64_t *> outStride;
+
+  // Transformed index (dimension above this object's) of each plane of the
+  // next convolvePlanes() batch; set by Convolution3 for user multipliers
+  // (reference convolve.h:1759: cyz->indices.index[1]=fftx->index(rx,i+base)).
+  std::vector<size_t> planeIndex;
 
 protected:
   DeviceArrays dev;   // staging of host inputs

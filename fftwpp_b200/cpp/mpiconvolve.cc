@@ -33,7 +33,7 @@ Convolution2MPI::Convolution2MPI(fftBase *fftx, fftBase *ffty,
     exit(-1);
   }
   d=split3(fftx->allRows(),ffty->L,1,group);
-  if(fftx->C != d.y) {
+  if(fftx->C != std::max<size_t>(d.y,1)) {
     std::cerr << "Convolution2MPI: fftx->C=" << fftx->C
               << " does not match the local slab width " << d.y << std::endl;
     exit(-1);
@@ -71,7 +71,7 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
   }
   size_t rowWords=ffty->S;          // words per y row (z extent incl. stride)
   d=split3(fftx->allRows(),ffty->L,rowWords,group);
-  if(fftx->C != d.y*rowWords) {
+  if(fftx->C != std::max<size_t>(d.y,1)*rowWords) {
     std::cerr << "Convolution3MPI: fftx->C=" << fftx->C
               << " does not match the local slab " << d.y << "x" << rowWords
               << std::endl;
@@ -93,7 +93,36 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
     fftx->p <= 2;
   const char *e=getenv("FFTWPP_MPI_FUSED");
   if(e && *e == '0') fused=false;
+  // kernel eligibility (fast plans present, register variant of the y pass)
+  // -- probed only where a communicator (hence a device) exists
+  if(fused && group.comm && d.y > 0)
+    fused=fftwpp_gpu_mapped_supported(fftx->plan(),0) == 1 &&
+      fftwpp_gpu_mapped_supported(ffty->plan(),1) == 1;
+  // The predicate depends on rank-local values (slab width, environment):
+  // all ranks must take the same path or they would wait in different
+  // collectives.  Reduce it (logical AND) over the group.
+  fused=agree(fused);
   fusedReady=false;
+}
+
+// Logical AND of a rank-local predicate over all ranks (collective).
+bool SlabTranspose::agree(bool mine)
+{
+  if(!group.comm || group.size <= 1) return mine;
+  void *st=gpu::stream();
+  DeviceArrays tmp;
+  tmp.ensure(2,sizeof(uint64_t)*group.size);
+  uint64_t v=mine ? 1 : 0;
+  std::vector<uint64_t> all(group.size);
+  gpu::check(fftwpp_gpu_memcpy_h2d(tmp.ptr[0],&v,sizeof(v),st),"h2d");
+  gpu::check(fftwpp_gpu_comm_allgather(group.comm,tmp.ptr[0],tmp.ptr[1],
+                                       sizeof(v),st),"all-gather (agree)");
+  gpu::check(fftwpp_gpu_memcpy_d2h(all.data(),tmp.ptr[1],
+                                   sizeof(v)*group.size,st),"d2h");
+  gpu::check(fftwpp_gpu_stream_sync(st),"sync");
+  bool ok=true;
+  for(int p=0; p < group.size; ++p) ok=ok && all[p] != 0;
+  return ok;
 }
 
 Convolution3MPI::~Convolution3MPI()
@@ -202,7 +231,7 @@ void SlabTranspose::runSlab(fftBase *fftx, size_t A, size_t B,
 {
   size_t N=std::max(A,B);
   void *st=gpu::stream();
-  if(!gpu::isDevice(f[0])) {
+  if(d.y > 0 && !gpu::isDevice(f[0])) {
     std::cerr << "distributed convolutions need device pointers" << std::endl;
     exit(-1);
   }
@@ -237,8 +266,9 @@ void SlabTranspose::runSlab(fftBase *fftx, size_t A, size_t B,
   gpu::check(fftwpp_gpu_stream_wait_event(commStream,evStart),"wait");
 
   for(size_t a=0; a < A; ++a) {
-    gpu::check(fftwpp_gpu_forward(fftx->plan(),0,nsub,1,f[a]+offset,
-                                  devF.ptr[a],1,0,0,st),"forward");
+    if(d.y > 0) // ranks without y rows have no local x pass
+      gpu::check(fftwpp_gpu_forward(fftx->plan(),0,nsub,1,f[a]+offset,
+                                    devF.ptr[a],1,0,0,st),"forward");
     gpu::check(fftwpp_gpu_event_record(evX[a],st),"event");
   }
   for(size_t c=0; c < nc; ++c) {
@@ -261,7 +291,7 @@ void SlabTranspose::runSlab(fftBase *fftx, size_t A, size_t B,
   }
   gpu::check(fftwpp_gpu_event_record(evB,commStream),"event");
   gpu::check(fftwpp_gpu_stream_wait_event(st,evB),"wait");
-  for(size_t b=0; b < B; ++b)
+  for(size_t b=0; b < B && d.y > 0; ++b)
     gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[b],
                                    f[b]+offset,0,sc,1,0,0,st),"backward");
 }
@@ -379,7 +409,7 @@ void Convolution3MPI::runFused(Complex **f, size_t offset, double sc)
   const std::vector<ResidueCall>& calls=fftx->calls();
   size_t nsub=calls.back().sb0+calls.back().nsb;
   const uint64_t *base=(const uint64_t *) devMap.ptr[0];
-  for(size_t a=0; a < A; ++a) {
+  for(size_t a=0; a < A && d.y > 0; ++a) {
     const uint64_t *m=base+a*2*d.X;
     gpu::check(fftwpp_gpu_forward_mapped(fftx->plan(),0,nsub,f[a]+offset,m,
                                          (const int64_t *) (m+d.X),1,0,st),
@@ -391,7 +421,7 @@ void Convolution3MPI::runFused(Complex **f, size_t offset, double sc)
   if(d.x > 0)
     convolveyz[0]->convolvePlanes(T.data(),0,d.x,d.Y*d.Z,1.0);
   gpu::check(fftwpp_gpu_comm_barrier(group.comm,st),"barrier");
-  for(size_t b=0; b < B; ++b)
+  for(size_t b=0; b < B && d.y > 0; ++b)
     gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[b],
                                    f[b]+offset,0,sc,1,0,0,st),"backward");
 }

@@ -98,6 +98,7 @@ protected:
                Complex **f, size_t offset, double scale,
                const InnerSweep& inner);
   void chunkRange(int rank, size_t c, size_t nc, size_t *lo, size_t *hi);
+  bool agree(bool mine);
   void transposeForward(void *Fx, void *T, size_t c, size_t nc, void *st);
   void transposeBackward(void *T, void *Fx, size_t c, size_t nc, void *st);
 };

@@ -347,6 +347,11 @@ int fftwpp_gpu_backward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
   return rc < 0 ? rc : 0;
 }
 
+int fftwpp_gpu_mapped_supported(fftwpp_gpu_plan *plan, int backward)
+{
+  return plan ? fast_mapped_supported((Plan *) plan,backward) : 0;
+}
+
 int fftwpp_gpu_ipc_get_handle(void *devptr, char *handle64)
 {
   cudaIpcMemHandle_t h;

@@ -127,7 +127,11 @@ int fftwpp_gpu_comm_create(int rank, int size, const char *id128, void **comm)
   }
   c->flag=NULL;
   cudaError_t e=cudaMalloc((void **) &c->flag,2*sizeof(int));
-  if(e != cudaSuccess) return cuda_fail(e,"cudaMalloc(barrier flag)");
+  if(e != cudaSuccess) {
+    g_nccl.CommDestroy(c->comm);
+    delete c;
+    return cuda_fail(e,"cudaMalloc(barrier flag)");
+  }
   cudaMemset(c->flag,0,2*sizeof(int));
   *comm=c;
   return 0;
@@ -202,19 +206,23 @@ int fftwpp_gpu_comm_alltoallv(void *comm, const void *send,
   }
   ncclResult_t r=g_nccl.GroupStart();
   if(r) return ncclFail(r,"ncclGroupStart");
-  for(int p=0; p < c->size; ++p) {
+  // a failing send/recv must not leave the NCCL group open for later calls
+  ncclResult_t bad=(ncclResult_t) 0;
+  const char *what=NULL;
+  for(int p=0; p < c->size && !bad; ++p) {
     if(p == me) continue;
     if(scount[p]) {
       r=g_nccl.Send((const char *) send+sdispl[p],scount[p],ncclChar,p,c->comm,
                     st);
-      if(r) return ncclFail(r,"ncclSend");
+      if(r) {bad=r; what="ncclSend"; break;}
     }
     if(rcount[p]) {
       r=g_nccl.Recv((char *) recv+rdispl[p],rcount[p],ncclChar,p,c->comm,st);
-      if(r) return ncclFail(r,"ncclRecv");
+      if(r) {bad=r; what="ncclRecv"; break;}
     }
   }
   r=g_nccl.GroupEnd();
+  if(bad) return ncclFail(bad,what);
   if(r) return ncclFail(r,"ncclGroupEnd");
   return 0;
 }

@@ -76,7 +76,15 @@ struct ConvPtrs {
   void *p[MAXARRAYS];
 };
 
-struct FastInfo; // fast_kernels.cu
+// What the specialised power-of-two kernels know about a plan
+// (fast_kernels.cu: fast_plan_init).
+struct FastInfo {
+  int log2m;        // m = 2^log2m: the longer of the (at most two) FFT lengths
+  bool uniform;     // every sub-block has length m
+  int nterm;        // max number of input terms folded into one W[s]
+  bool pairable;    // REAL plans: every full-length sub-block is an r2c block,
+                    // so two adjacent real columns share one complex FFT
+};
 
 struct Plan {
   fftwpp_gpu_pad_desc desc;
@@ -148,6 +156,18 @@ int fast_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
 int fast_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
                       int mult, double scale, uint64_t nrows, uint64_t rs,
                       cudaStream_t st);
+int fast_mapped_supported(Plan *pl, int backward);
+
+// TMA-staged strided passes (tma_kernels.cu): tiles move between HBM and
+// shared memory with cp.async.bulk.tensor (tensor maps built per launch),
+// completion on mbarriers.  Same return convention as fast_try_*.
+int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                    const void *f, void *F, uint64_t nrows, uint64_t frs,
+                    uint64_t Frs, cudaStream_t st);
+int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
+                     const void *F, void *f, int accumulate, double scale,
+                     uint64_t nrows, uint64_t Frs, uint64_t frs,
+                     cudaStream_t st);
 
 } // namespace fftwpp_gpu
 

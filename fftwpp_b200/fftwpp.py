@@ -16,7 +16,12 @@ import ctypes
 import numpy as np
 from numpy.ctypeslib import ndpointer
 
-from ._lib import lib as clib
+from ._lib import lib_path
+
+# a private handle: its prototypes (numpy ndpointer arguments, as in the
+# reference module) do not disturb the package-wide ctypes signatures
+clib = ctypes.CDLL(lib_path)
+clib.get_fftwpp_maxthreads.restype = ctypes.c_size_t
 
 __all__ = ["Convolution", "HConvolution", "complex_align",
            "fftwpp_set_maxthreads", "fftwpp_get_maxthreads"]

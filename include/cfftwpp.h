@@ -137,6 +137,15 @@ void *fftwpp_conv_create_custom(int dim, int family, const size_t *L,
                                 fftwpp_multiplier *host,
                                 fftwpp_device_multiplier *device);
 void fftwpp_indices_get(void *indices, size_t *r, size_t *offset);
+/* The transformed multi-index the reference hands to multipliers through
+ * `Indices` (convolve.h:48-76; use shown at convolve.cc:39-48): size = number
+ * of OUTER dimensions (0 in 1-D, 1 in 2-D, 2 in 3-D); outer(d) = indices->
+ * index[d], set per transformed row by each outer level (convolve.h:1442,1759;
+ * d = size-1 is the outermost, x); index(j) = fft->index(r,j+offset), the
+ * transformed index of element j of this block in the innermost dimension. */
+size_t fftwpp_indices_size(void *indices);
+size_t fftwpp_indices_outer(void *indices, size_t d);
+size_t fftwpp_indices_index(void *indices, size_t j);
 void fftwpp_conv_destroy(void *conv);
 /* out = {m,p,q,n,D,inplace,C,S} of dimension d */
 void fftwpp_conv_params(void *conv, int d, size_t *out);

@@ -192,6 +192,10 @@ int fftwpp_gpu_backward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
                                const int64_t *rowstride, uint64_t plane0,
                                double scale, uint64_t nrows,
                                uint64_t F_rowstride, void *stream);
+/* 1 if the plan's forward (backward != 0: backward) pass can run with a row
+ * map, 0 if not (no kernel is launched).  Ranks of a distributed convolution
+ * agree on the fused exchange by reducing this predicate. */
+int fftwpp_gpu_mapped_supported(fftwpp_gpu_plan *plan, int backward);
 /* CUDA IPC: export a cudaMalloc'ed buffer / map a peer's buffer (64-byte
  * handles, exchanged by any means) */
 int fftwpp_gpu_ipc_get_handle(void *devptr, char *handle64);

@@ -135,3 +135,74 @@ def test_custom_binary_2d_device_arrays(dev):
     torch.cuda.synchronize()
     assert O.rel_l2(a[0].cpu().numpy(), want) < 1e-12
     conv.close()
+
+
+# ---------------------------------------------------------------------------
+# index-aware multipliers (reference Indices, convolve.h:48-76; the outer
+# levels set indices.index[d] per transformed row, convolve.h:1442,1759; the
+# innermost index is fft->index(r,j+offset), convolve.cc:39-48)
+# ---------------------------------------------------------------------------
+
+def _weight(*k):
+    """Some function of the transformed multi-index (kx[,ky[,kz]])."""
+    t = sum((d + 2) * np.asarray(kk) for d, kk in enumerate(k))
+    return 1.0 / (1.0 + (t % 7)) + 0.25j * ((t % 5) - 2)
+
+
+def _filtered_oracle(f, g, padded):
+    """fft(F G W)/N restricted to [0,L): forward sign +1 (convolve.cc:576),
+    F = explicit padded DFT, W evaluated on the padded index grid."""
+    ax = tuple(range(f.ndim))
+    N = int(np.prod(padded))
+    F = np.fft.ifftn(f, padded, axes=ax) * N
+    G = np.fft.ifftn(g, padded, axes=ax) * N
+    grids = np.meshgrid(*[np.arange(n) for n in padded], indexing="ij")
+    h = np.fft.fftn(F * G * _weight(*grids), axes=ax) / N
+    return h[tuple(slice(0, n) for n in f.shape)]
+
+
+def _indexed_host(F, n, ctx):
+    kin = np.array([ctx.index(j) for j in range(n)])
+    outer = ctx.outer[::-1]          # reference order: outermost (x) last
+    F[0][:] = F[0] * F[1] * _weight(*outer, kin)
+
+
+def _indexed_device(ptrs, n, ctx, stream):
+    kin = np.array([ctx.index(j) for j in range(n)])
+    w = torch.from_numpy(np.asarray(_weight(*ctx.outer[::-1], kin), dtype=np.complex128)).cuda()
+    a, b = _dev(ptrs[0], n), _dev(ptrs[1], n)
+    a.mul_(b).mul_(w)
+
+
+@pytest.mark.parametrize("dev", [False, True])
+@pytest.mark.parametrize("L,M,m,D", [((12,), (24,), None, None), ((12,), (30,), (4,), (1,)),
+                                     ((8,), (32,), (8,), (2,)),
+                                     ((6, 8), (12, 16), None, None), ((6, 8), (12, 20), (3, 4), (1, 1)),
+                                     ((4, 5, 6), (8, 10, 12), None, None),
+                                     ((4, 6, 8), (8, 12, 16), (2, 6, 4), (1, 1, 2))])
+def test_index_aware_multiplier(L, M, m, D, dev):
+    rng = np.random.default_rng(sum(L) + sum(M))
+    f, g = crand(rng, *L), crand(rng, *L)
+    conv = fp.HybridConv(list(L), list(M), m=m, D=D, I=None if m is None else [0] * len(L),
+                         mult=_indexed_host, device_mult=_indexed_device if dev else None,
+                         indexed=True)
+    padded = [conv.params(d)["m"] * conv.params(d)["q"] for d in range(len(L))]
+    want = _filtered_oracle(f, g, padded)
+    a = [np.ascontiguousarray(f.copy()), np.ascontiguousarray(g.copy())]
+    conv.convolve(a)
+    assert O.rel_l2(a[0], want) < 1e-12, [conv.params(d) for d in range(len(L))]
+    conv.close()
+
+
+def test_many_arrays_beyond_fused_limit():
+    """A=10 > 8 arrays: the built-in multNone runs on the unfused path instead
+    of overflowing the fused kernels' argument block."""
+    L, A = 16, 10
+    rng = np.random.default_rng(3)
+    arrays = [crand(rng, L) for _ in range(A)]
+    keep = [a.copy() for a in arrays]
+    conv = fp.HybridConv([L], [2 * L], A=A, B=A, mult=fp.MULT_NONE)
+    conv.convolve(arrays)
+    for a, k in zip(arrays, keep):
+        assert O.rel_l2(a, k) < 1e-12
+    conv.close()
