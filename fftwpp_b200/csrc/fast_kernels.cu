@@ -350,6 +350,124 @@ fast_conv_rows_pipe(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   }
 }
 
+// The same software pipeline specialised for the shape of every BASELINE z
+// pass: fftPad with p=1, q=2 (sub-blocks k0=0 and k0=1) and full rows (L == m).
+// No per-point bounds or residue predicates, and the residue twiddles are not
+// read from a table per point: zeta^{tau+TPT t} = zeta^tau (zeta^TPT)^t by
+// successive products from one shared-memory word per thread and a kernel
+// constant (the shared-memory pipe, not FP64 issue, is the busier one: this
+// removes 21 of the 24 128-bit residue-twiddle reads per row).
+template<int LG, int MULT>
+__global__ void __launch_bounds__((1 << LG)/8 > 256 ? (1 << LG)/8 : 256, (1 << LG)/8 > 256 ? 1 : 2)
+fast_conv_rows_q2(PlanDev P, const SubBlockDev *__restrict__ sbs,
+                  double2 *f0, const double2 *f1, double scale,
+                  const double2 zstep, long long nrows, long long rs,
+                  int tabid, long long ngroups)
+{
+  typedef WFFT<LG> FFT;
+  typedef RegFFT<LG> RF;
+  const int M=1 << LG;
+  const int TPT=M/8;
+  const int NT=TPT > 256 ? TPT : 256;
+  const int ROWS=NT/TPT;
+  const int BUF=M+M/8;
+  const int TWN=RF::twCount();
+  extern __shared__ __align__(16) double2 sm[];
+  double2 *tws=sm;
+  double2 *bufs=sm+TWN;
+  const int rowInCta=threadIdx.x/TPT;
+  const int tau=threadIdx.x % TPT;
+  for(int i=threadIdx.x; i < TWN; i += NT) tws[i]=__ldg(P.tab[tabid].tw8+i);
+  __syncthreads();
+  double2 *zs=bufs;
+  bufs += TPT;
+  for(int i=threadIdx.x; i < TPT; i += NT) zs[i]=zeta(P,modN(P,sbs[1].k0,i));
+  __syncthreads();
+
+  RowLayout lay;
+  lay.base=rowInCta*2*BUF;
+  lay.barid=TPT > 32 ? 1+rowInCta : 0;
+  lay.nthreads=TPT;
+  double2 *park=bufs+lay.base+BUF+tau;
+
+  long long grp=blockIdx.x;
+  if(grp >= ngroups) return;
+  double2 x[1][8], y[1][8];
+  {
+    long long row=grp*ROWS+rowInCta;
+    if(row >= nrows) row=nrows-1;
+    const double2 *g1=f1+row*rs+tau;
+#pragma unroll
+    for(int t=0; t < 8; ++t) y[0][t]=g1[TPT*t];
+  }
+  for(; grp < ngroups; grp += gridDim.x) {
+    long long row=grp*ROWS+rowInCta;
+    const bool live=row < nrows;
+    if(!live) row=nrows-1;
+    double2 *g0=f0+row*rs+tau;
+    const double2 *g1=f1+row*rs+tau;
+    const long long ngrp=grp+gridDim.x;
+    const bool more=ngrp < ngroups;
+    long long nrow=ngrp*ROWS+rowInCta;
+    if(nrow >= nrows) nrow=nrows-1;
+    const double2 *n1=f1+nrow*rs+tau;
+    if(more) {
+      const char *p0=(const char *) (f0+nrow*rs);
+      const char *p1=(const char *) (f1+nrow*rs);
+      for(int off=tau*128; off < M*16; off += TPT*128) {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
+      }
+    }
+#pragma unroll 1
+    for(int isb=0; isb < 2; ++isb) {
+      const bool hz=isb == 1;
+#pragma unroll
+      for(int t=0; t < 8; ++t) x[0][t]=g0[TPT*t];
+      if(hz) {
+        double2 z=zs[tau];
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          y[0][t]=fmul(y[0][t],z);
+          if(t < 7) z=fmul(z,zstep);
+        }
+      }
+      RF::template forward<1,RowLayout,true,false,2>(y,tau,tws,bufs,0,lay,true);
+      if(hz) {
+        double2 z=zs[tau];
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          x[0][t]=fmul(x[0][t],z);
+          if(t < 7) z=fmul(z,zstep);
+        }
+      }
+      RF::template forward<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        x[0][t]=MULT == FFTWPP_MULT_BINARY ? fmul(x[0][t],y[0][t]) : fmulc(x[0][t],y[0][t]);
+      if(!hz || more) {
+        const double2 *h1=hz ? n1 : g1;
+#pragma unroll
+        for(int t=0; t < 8; ++t) y[0][t]=h1[TPT*t];
+      }
+      RF::template adjoint<1,RowLayout,true,false,2>(x,tau,tws,bufs,0,lay,true);
+      if(!hz) {
+#pragma unroll
+        for(int t=0; t < 8; ++t) park[t*TPT]=x[0][t];
+      } else {
+        double2 z=zs[tau];
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          double2 v=fmulc(x[0][t],z)+park[t*TPT];
+          if(t < 7) z=fmul(z,zstep);
+          if(live) g0[TPT*t]=make_double2(v.x*scale,v.y*scale);
+        }
+      }
+    }
+  }
+}
+
+
 // ---------------------------------------------------------------------------
 // One-warp transforms of length 512: 16 points per thread
 // ---------------------------------------------------------------------------
@@ -1514,6 +1632,17 @@ bool convPipeEnabled()
   return on == 1;
 }
 
+// FFTWPP_CONV_Q2=0: keep p=1, q=2 rows on the general pipelined kernel (A/B)
+bool convQ2Disabled()
+{
+  static int off=-1;
+  if(off < 0) {
+    const char *s=getenv("FFTWPP_CONV_Q2");
+    off=(s && *s == '0') ? 1 : 0;
+  }
+  return off == 1;
+}
+
 // FFTWPP_THREE_CTAS=0: compile-bound the gathering real forward pass for two
 // CTAs per SM instead of three (A/B switch)
 bool threeCtasEnabled()
@@ -1768,6 +1897,34 @@ int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
          zl);
     }
     rc=check_launch("fast_conv_rows_warp",st);
+    return rc ? rc : 1;
+  }
+  // p=1, q=2, full rows: the straight-line kernel with register twiddles
+  if(NTERM == 1 && convPipeEnabled() && !convQ2Disabled() &&
+     pl->hsub.size() == 2 && pl->hsub[0].k0 == 0 && pl->hsub[1].k0 != 0 &&
+     pl->dev.jmax == M && pl->dev.jmin == 0 &&
+     (mult == FFTWPP_MULT_BINARY || mult == FFTWPP_MULT_CORRELATION)) {
+    size_t sm2=((size_t) twn+TPT+2*(size_t) ROWS*BUF)*sizeof(double2);
+    if(sm2 > SMEM_MAX) return 0;
+    // zeta_N^{k0 TPT}, the step between a thread's successive points
+    const long double ang=2.0L*3.141592653589793238462643383279502884L*
+      (long double) ((pl->hsub[1].k0*(unsigned long long) TPT) %
+                     (unsigned long long) pl->dev.N)/(long double) pl->dev.N;
+    const double2 zstep=make_double2((double) cosl(ang),(double) sinl(ang));
+#define CALLQ(LGV, MU)                                                       \
+    rc=allowSmem(fast_conv_rows_q2<LGV,MU>);                                 \
+    if(rc) return rc;                                                        \
+    prof_begin(4*pl->tag+2,st);                                              \
+    fast_conv_rows_q2<LGV,MU><<<(unsigned) grid,NT,sm2,st>>>                 \
+      (pl->dev,pl->dsub,(double2 *) f[0],(const double2 *) f[1],scale,       \
+       zstep,(long long) nrows,(long long) rs,tabid,(long long) ngroups);
+#define CALL(LGV)                                                            \
+    if(mult == FFTWPP_MULT_BINARY) {CALLQ(LGV,FFTWPP_MULT_BINARY)}           \
+    else {CALLQ(LGV,FFTWPP_MULT_CORRELATION)}
+    LG_CASES(CALL)
+#undef CALL
+#undef CALLQ
+    rc=check_launch("fast_conv_rows_q2",st);
     return rc ? rc : 1;
   }
   if(NTERM == 1 && convPipeEnabled()) {

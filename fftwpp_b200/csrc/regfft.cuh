@@ -338,6 +338,109 @@ __device__ __forceinline__ double2 ozeta(const PlanDev& P, long long e)
 }
 
 
+// Register FFT with the radix-8 twiddle base of every pass held in registers
+// (persistent CTAs: loaded once); w^2..w^7 are products.
+template<int LG>
+struct WFFT {
+  typedef RegFFT<LG> F;
+  static const int NR8=F::NR8;
+
+  static __device__ __forceinline__ void loadW(const double2 *tw8, int tau,
+                                               double2 (&w1)[NR8 > 0 ? NR8 : 1])
+  {
+#pragma unroll
+    for(int i=0; i < NR8; ++i) {
+      const int ls=LG-3*(i+1);
+      w1[i]=ls > 0 ? __ldg(tw8+F::twOff(i)+(tau & ((1 << ls)-1))) :
+        make_double2(1.0,0.0);
+    }
+  }
+
+  static __device__ __forceinline__ void powers(double2 w1, double2 (&w)[8])
+  {
+    w[1]=w1;
+    w[2]=fmul(w[1],w[1]);
+    w[3]=fmul(w[1],w[2]);
+    w[4]=fmul(w[2],w[2]);
+    w[5]=fmul(w[1],w[4]);
+    w[6]=fmul(w[3],w[3]);
+    w[7]=fmul(w[3],w[4]);
+  }
+
+  template<class Lay>
+  static __device__ __forceinline__ void exchange(double2 (&x)[8], int tau,
+                                                  int lsFrom, int lsTo,
+                                                  double2 *buf, const Lay& lay)
+  {
+    lay.sync();
+#pragma unroll
+    for(int t=0; t < 8; ++t) buf[lay.addr(F::pos(tau,t,lsFrom))]=x[t];
+    lay.sync();
+#pragma unroll
+    for(int t=0; t < 8; ++t) x[t]=buf[lay.addr(F::pos(tau,t,lsTo))];
+  }
+
+  // in: x[t]=W[tau+TPT*t]; out: x[e] at scrambled position 8*tau+e
+  template<class Lay>
+  static __device__ __forceinline__ void forward(double2 (&x)[8], int tau,
+                                                 const double2 (&w1)[NR8 > 0 ? NR8 : 1],
+                                                 double2 *buf, const Lay& lay)
+  {
+#pragma unroll
+    for(int i=0; i < NR8; ++i) {
+      const int ls=LG-3*(i+1);
+      bfly8<1>(x);
+      if(ls > 0) {
+        double2 w[8];
+        powers(w1[i],w);
+#pragma unroll
+        for(int u=1; u < 8; ++u) x[u]=fmul(x[u],w[u]);
+      }
+      const int lsNext=(i+1 < NR8) ? LG-3*(i+2) : 0;
+      if(i+1 < NR8 || F::REM > 0) exchange(x,tau,ls,lsNext,buf,lay);
+    }
+    if(F::REM == 2) {
+      bfly4<1>(x[0],x[1],x[2],x[3]);
+      bfly4<1>(x[4],x[5],x[6],x[7]);
+    } else if(F::REM == 1) {
+      bfly2(x[0],x[1]);
+      bfly2(x[2],x[3]);
+      bfly2(x[4],x[5]);
+      bfly2(x[6],x[7]);
+    }
+  }
+
+  // exact adjoint of forward()
+  template<class Lay>
+  static __device__ __forceinline__ void adjoint(double2 (&x)[8], int tau,
+                                                 const double2 (&w1)[NR8 > 0 ? NR8 : 1],
+                                                 double2 *buf, const Lay& lay)
+  {
+    if(F::REM == 2) {
+      bfly4<-1>(x[0],x[1],x[2],x[3]);
+      bfly4<-1>(x[4],x[5],x[6],x[7]);
+    } else if(F::REM == 1) {
+      bfly2(x[0],x[1]);
+      bfly2(x[2],x[3]);
+      bfly2(x[4],x[5]);
+      bfly2(x[6],x[7]);
+    }
+#pragma unroll
+    for(int i=NR8-1; i >= 0; --i) {
+      const int ls=LG-3*(i+1);
+      const int lsPrev=(i+1 < NR8) ? LG-3*(i+2) : 0;
+      if(i+1 < NR8 || F::REM > 0) exchange(x,tau,lsPrev,ls,buf,lay);
+      if(ls > 0) {
+        double2 w[8];
+        powers(w1[i],w);
+#pragma unroll
+        for(int u=1; u < 8; ++u) x[u]=fmulc(x[u],w[u]);
+      }
+      bfly8<-1>(x);
+    }
+  }
+};
+
 } // namespace
 } // namespace fftwpp_gpu
 
