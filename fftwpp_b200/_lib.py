@@ -47,6 +47,8 @@ for _n in ("increment", "blocksize", "noutputs", "span"):
 _sig("fftwpp_pad_index", c_size_t, c_void_p, c_size_t, c_size_t)
 _sig("fftwpp_pad_forward", None, c_void_p, c_void_p, c_void_p, c_size_t)
 _sig("fftwpp_pad_backward", None, c_void_p, c_void_p, c_void_p, c_size_t)
+_sig("fftwpp_pad_forward_split", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
+_sig("fftwpp_pad_backward_split", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_double)
 _sig("fftwpp_conv_create", c_void_p, c_int, c_int, P(c_size_t), P(c_size_t),
      P(c_size_t), P(c_size_t), P(c_long), c_size_t, c_size_t, c_size_t, c_size_t, c_int)
 _sig("fftwpp_conv_destroy", None, c_void_p)
@@ -92,6 +94,8 @@ _sig("fftwpp_mpiconv3_destroy", None, c_void_p)
 _sig("fftwpp_mpiconv3_split", None, c_void_p, P(c_size_t))
 _sig("fftwpp_mpiconv3_params", None, c_void_p, c_int, P(c_size_t))
 _sig("fftwpp_mpiconv3_convolve", None, c_void_p, P(c_void_p), c_int)
+_sig("fftwpp_mpiconv3_convolve_async", None, c_void_p, P(c_void_p), c_int, c_int)
+_sig("fftwpp_mpiconv3_wait", None, c_void_p, c_int)
 _sig("fftwpp_mpiconv3_exchange_table", None, c_void_p, c_int, P(ctypes.c_ulonglong),
      P(ctypes.c_ulonglong), P(ctypes.c_ulonglong), P(ctypes.c_ulonglong))
 _sig("fftwpp_mpiconv3_set_plane_chunk", None, c_void_p, c_size_t)

@@ -351,6 +351,57 @@ void fftwpp_pad_backward(void *pad, const double *F, double *f, size_t r)
   ((Pad *) pad)->fft->backward((Complex *) F,(Complex *) f,r);
 }
 
+// All-residues forward / backward pass with the OUTPUT rows split among
+// `nsplit` owners of ceil-split row ranges (the slab decomposition's
+// localdimension), every owner's range living in the same dense DEVICE buffer:
+// the destination-set machinery of the fused exchange on one GPU.  The result
+// must equal the plain all-residues pass.  Returns 0, or
+// FFTWPP_GPU_EUNSUPPORTED when the plan has no TMA-staged kernel.
+int fftwpp_pad_forward_split(void *pad, const void *f, void *F, size_t nsplit)
+{
+  fftBase *fft=((Pad *) pad)->fft;
+  const std::vector<ResidueCall>& calls=fft->calls();
+  size_t nsub=calls.back().sb0+calls.back().nsb;
+  size_t rows=fft->allRows();
+  std::vector<fftwpp_gpu_dest> d;
+  for(size_t p=0; p < nsplit; ++p) {
+    size_t r0;
+    size_t n=utils::localdimension(rows,p,nsplit,&r0);
+    fftwpp_gpu_dest t;
+    t.base=(Complex *) F+r0*fft->S;
+    t.row0=r0;
+    t.rows=n;
+    t.row_stride=fft->S;
+    t.plane_stride=0;
+    d.push_back(t);
+  }
+  return fftwpp_gpu_forward_dests(fft->plan(),0,nsub,f,d.data(),(int) d.size(),
+                                  0,1,0,gpu::stream());
+}
+
+int fftwpp_pad_backward_split(void *pad, const void *F, void *f, size_t nsplit,
+                              double scale)
+{
+  fftBase *fft=((Pad *) pad)->fft;
+  const std::vector<ResidueCall>& calls=fft->calls();
+  size_t nsub=calls.back().sb0+calls.back().nsb;
+  size_t rows=fft->inputLength();
+  std::vector<fftwpp_gpu_dest> d;
+  for(size_t p=0; p < nsplit; ++p) {
+    size_t r0;
+    size_t n=utils::localdimension(rows,p,nsplit,&r0);
+    fftwpp_gpu_dest t;
+    t.base=(Complex *) f+r0*fft->S;
+    t.row0=r0;
+    t.rows=n;
+    t.row_stride=fft->S;
+    t.plane_stride=0;
+    d.push_back(t);
+  }
+  return fftwpp_gpu_backward_dests(fft->plan(),0,nsub,F,d.data(),
+                                   (int) d.size(),0,scale,1,0,gpu::stream());
+}
+
 void *fftwpp_conv_create(int dim, int family, const size_t *L, const size_t *M,
                          const size_t *m, const size_t *D, const long *I,
                          size_t Sx, size_t Sy, size_t A, size_t B, int mult)
@@ -486,13 +537,40 @@ struct MpiConv {
   fftBase *fft[3];
   Convolution2MPI *conv2;
   Convolution3MPI *conv3;
-  MpiConv() : dim(0), conv2(NULL), conv3(NULL) {
+  size_t A,B;
+  size_t slabBytes; // bytes of one local input slab
+  // pipelined host-buffer entry (fftwpp_mpiconv3_convolve_async)
+  void *h2d,*d2h;
+  void *evIn[2],*evDone[2],*evOut[2];
+  bool busy[2];
+  DeviceArrays slotBuf[2];
+  MpiConv() : dim(0), conv2(NULL), conv3(NULL), A(0), B(0), slabBytes(0),
+              h2d(NULL), d2h(NULL) {
     for(int d=0; d < 3; ++d) {app[d]=NULL; fft[d]=NULL;}
+    busy[0]=busy[1]=false;
   }
   ~MpiConv() {
+    if(h2d) {
+      fftwpp_gpu_stream_destroy(h2d);
+      fftwpp_gpu_stream_destroy(d2h);
+      for(int s=0; s < 2; ++s) {
+        fftwpp_gpu_event_destroy(evIn[s]);
+        fftwpp_gpu_event_destroy(evDone[s]);
+        fftwpp_gpu_event_destroy(evOut[s]);
+      }
+    }
     delete conv2;
     delete conv3;
     for(int d=2; d >= 0; --d) {delete fft[d]; delete app[d];}
+  }
+  void run(Complex **f, bool normalized) {
+    if(conv3) {
+      if(normalized) conv3->convolve(f);
+      else conv3->convolveRaw(f);
+    } else {
+      if(normalized) conv2->convolve(f);
+      else conv2->convolveRaw(f);
+    }
   }
   SlabTranspose *slab() {
     return conv3 ? (SlabTranspose *) conv3 : (SlabTranspose *) conv2;
@@ -577,6 +655,9 @@ MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
     c->fft[2]=makePad(kinds[2],L[2],M[2],*c->app[2],1,0,m[2],D[2],I[2]);
     c->conv3=new Convolution3MPI(c->fft[0],c->fft[1],c->fft[2],group);
   }
+  c->A=A;
+  c->B=B;
+  c->slabBytes=L[0]*y*rowWords*(family == 2 ? sizeof(double) : sizeof(Complex));
   return c;
 }
 }
@@ -624,14 +705,60 @@ void fftwpp_mpiconv2_params(void *conv, int d, size_t *out)
 
 void fftwpp_mpiconv3_convolve(void *conv, double **f, int normalized)
 {
+  ((MpiConv *) conv)->run((Complex **) f,normalized != 0);
+}
+
+// Pipelined form for PINNED HOST slabs: every rank copies its own slabs over
+// its own PCIe link on a side stream, convolves on the compute stream (the
+// exchanges are stream-ordered collectives there) and copies the result back
+// on a third stream.  Two slots: alternate them so that one convolution's
+// transfers overlap the other's compute.  COLLECTIVE: all ranks must call it
+// in the same order.
+void fftwpp_mpiconv3_convolve_async(void *conv, double **f, int normalized,
+                                    int slot)
+{
   MpiConv *c=(MpiConv *) conv;
-  if(c->conv3) {
-    if(normalized) c->conv3->convolve((Complex **) f);
-    else c->conv3->convolveRaw((Complex **) f);
-  } else {
-    if(normalized) c->conv2->convolve((Complex **) f);
-    else c->conv2->convolveRaw((Complex **) f);
+  if(slot < 0 || slot > 1) {
+    std::cerr << "fftwpp_mpiconv3_convolve_async: slot must be 0 or 1"
+              << std::endl;
+    exit(-1);
   }
+  if(!c->h2d) {
+    gpu::check(fftwpp_gpu_stream_create(&c->h2d),"stream creation");
+    gpu::check(fftwpp_gpu_stream_create(&c->d2h),"stream creation");
+    for(int s=0; s < 2; ++s) {
+      gpu::check(fftwpp_gpu_event_create(&c->evIn[s]),"event creation");
+      gpu::check(fftwpp_gpu_event_create(&c->evDone[s]),"event creation");
+      gpu::check(fftwpp_gpu_event_create(&c->evOut[s]),"event creation");
+    }
+  }
+  size_t N=std::max(c->A,c->B);
+  size_t bytes=c->slabBytes;
+  c->slotBuf[slot].ensure(N,std::max<size_t>(bytes,16));
+  void *st=gpu::stream();
+  if(c->busy[slot])
+    gpu::check(fftwpp_gpu_stream_wait_event(c->h2d,c->evOut[slot]),"wait");
+  std::vector<Complex *> d(N);
+  for(size_t a=0; a < N; ++a) d[a]=(Complex *) c->slotBuf[slot].ptr[a];
+  for(size_t a=0; a < c->A && bytes; ++a)
+    gpu::check(fftwpp_gpu_memcpy_h2d(d[a],f[a],bytes,c->h2d),"h2d");
+  gpu::check(fftwpp_gpu_event_record(c->evIn[slot],c->h2d),"event");
+  gpu::check(fftwpp_gpu_stream_wait_event(st,c->evIn[slot]),"wait");
+  c->run(d.data(),normalized != 0);
+  gpu::check(fftwpp_gpu_event_record(c->evDone[slot],st),"event");
+  gpu::check(fftwpp_gpu_stream_wait_event(c->d2h,c->evDone[slot]),"wait");
+  for(size_t b=0; b < c->B && bytes; ++b)
+    gpu::check(fftwpp_gpu_memcpy_d2h(f[b],d[b],bytes,c->d2h),"d2h");
+  gpu::check(fftwpp_gpu_event_record(c->evOut[slot],c->d2h),"event");
+  c->busy[slot]=true;
+}
+
+void fftwpp_mpiconv3_wait(void *conv, int slot)
+{
+  MpiConv *c=(MpiConv *) conv;
+  if(slot < 0 || slot > 1 || !c->busy[slot]) return;
+  gpu::check(fftwpp_gpu_event_sync(c->evOut[slot]),"event sync");
+  c->busy[slot]=false;
 }
 void fftwpp_mpiconv2_convolve(void *conv, double **f, int normalized)
 {

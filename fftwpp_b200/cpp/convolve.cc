@@ -1347,10 +1347,17 @@ void Convolution2::convolvePlanes(Complex **F, size_t offset, size_t nplanes,
       if(bq < outBase.size() && outBase[bq]) {
         // offset is in words of F; planes are planestride words apart
         size_t plane0=(planestride ? offset/planestride : 0)+i0;
-        gpu::check(fftwpp_gpu_backward_mapped(fftx->plan(),0,nsub,devF.ptr[bq],
-                                              outBase[bq],outStride[bq],plane0,
-                                              sc,np,wordsPerPlane,st),
-                   "backward (fused exchange)");
+        int rc=FFTWPP_GPU_EUNSUPPORTED;
+        if(bq < outDests.size() && !outDests[bq].empty())
+          rc=fftwpp_gpu_backward_dests(fftx->plan(),0,nsub,devF.ptr[bq],
+                                       outDests[bq].data(),
+                                       (int) outDests[bq].size(),plane0,sc,np,
+                                       wordsPerPlane,st);
+        if(rc == FFTWPP_GPU_EUNSUPPORTED)
+          rc=fftwpp_gpu_backward_mapped(fftx->plan(),0,nsub,devF.ptr[bq],
+                                        outBase[bq],outStride[bq],plane0,sc,
+                                        np,wordsPerPlane,st);
+        gpu::check(rc,"backward (fused exchange)");
         continue;
       }
       char *dst=(char *) (F[bq]+offset)+

@@ -40,6 +40,7 @@
 #include "Array.h"
 
 struct fftwpp_gpu_plan;
+#include "../../include/fftwpp_gpu.h"
 
 namespace fftwpp {
 
@@ -497,6 +498,9 @@ public:
   // of back into F[b] (device arrays; see fftwpp_gpu_backward_mapped).
   std::vector<const uint64_t *> outBase;
   std::vector<const int64_t *> outStride;
+  // The same destinations as per-owner row ranges (fftwpp_gpu_backward_dests:
+  // bulk tensor stores issued by the TMA unit); tried first.
+  std::vector<std::vector<fftwpp_gpu_dest> > outDests;
 
   // Transformed index (dimension above this object's) of each plane of the
   // next convolvePlanes() batch; set by Convolution3 for user multipliers

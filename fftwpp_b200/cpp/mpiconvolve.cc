@@ -382,6 +382,34 @@ void Convolution3MPI::setupFused()
     }
     pos += 2*bwdLen;
   }
+  // the same destinations as per-peer row ranges for the TMA-staged kernels
+  // (fftwpp_gpu_forward_dests / backward_dests): one tensor map per peer
+  fwdDests.assign(A,std::vector<fftwpp_gpu_dest>());
+  for(size_t a=0; a < A; ++a)
+    for(int p=0; p < P; ++p) {
+      size_t px0;
+      size_t px=localdimension(d.X,p,P,&px0);
+      fftwpp_gpu_dest t;
+      t.base=(Complex *) peerT[(size_t) p*N+a]+d.y0*d.Z;
+      t.row0=px0;
+      t.rows=px;
+      t.row_stride=d.Y*d.Z;
+      t.plane_stride=0;
+      fwdDests[a].push_back(t);
+    }
+  convolveyz[0]->outDests.assign(B,std::vector<fftwpp_gpu_dest>());
+  for(size_t b=0; b < B; ++b)
+    for(int p=0; p < P; ++p) {
+      size_t py0;
+      size_t py=localdimension(d.Y,p,P,&py0);
+      fftwpp_gpu_dest t;
+      t.base=(Complex *) peerF[(size_t) p*B+b]+d.x0*py*d.Z;
+      t.row0=py0;
+      t.rows=py;
+      t.row_stride=d.Z;
+      t.plane_stride=py*d.Z;
+      convolveyz[0]->outDests[b].push_back(t);
+    }
   devMap.ensure(1,words*sizeof(uint64_t));
   gpu::check(fftwpp_gpu_memcpy_h2d(devMap.ptr[0],host.data(),
                                    words*sizeof(uint64_t),st),"h2d");
@@ -410,10 +438,17 @@ void Convolution3MPI::runFused(Complex **f, size_t offset, double sc)
   size_t nsub=calls.back().sb0+calls.back().nsb;
   const uint64_t *base=(const uint64_t *) devMap.ptr[0];
   for(size_t a=0; a < A && d.y > 0; ++a) {
-    const uint64_t *m=base+a*2*d.X;
-    gpu::check(fftwpp_gpu_forward_mapped(fftx->plan(),0,nsub,f[a]+offset,m,
-                                         (const int64_t *) (m+d.X),1,0,st),
-               "forward (fused exchange)");
+    // TMA bulk stores to the owners' buffers where the plan has such a
+    // kernel, else per-thread stores through the row maps
+    int rc=fftwpp_gpu_forward_dests(fftx->plan(),0,nsub,f[a]+offset,
+                                    fwdDests[a].data(),(int) fwdDests[a].size(),
+                                    0,1,0,st);
+    if(rc == FFTWPP_GPU_EUNSUPPORTED) {
+      const uint64_t *m=base+a*2*d.X;
+      rc=fftwpp_gpu_forward_mapped(fftx->plan(),0,nsub,f[a]+offset,m,
+                                   (const int64_t *) (m+d.X),1,0,st);
+    }
+    gpu::check(rc,"forward (fused exchange)");
   }
   gpu::check(fftwpp_gpu_comm_barrier(group.comm,st),"barrier");
   std::vector<Complex *> T(N);
@@ -428,7 +463,7 @@ void Convolution3MPI::runFused(Complex **f, size_t offset, double sc)
 
 void Convolution3MPI::HermitianSymmetrizeXY(Complex *f)
 {
-  if(!gpu::isDevice(f)) {
+  if(d.y > 0 && !gpu::isDevice(f)) {
     std::cerr << "distributed convolutions need device pointers" << std::endl;
     exit(-1);
   }
@@ -440,7 +475,7 @@ void Convolution3MPI::HermitianSymmetrizeXY(Complex *f)
   const size_t w=sizeof(Complex);
   // z=0 entries of the local slab, padded to ymax rows of y per x
   std::vector<Complex> mine(n,Complex(0.0,0.0)), all(n*P);
-  for(size_t i=0; i < Lx; ++i)
+  for(size_t i=0; i < Lx && dy > 0; ++i)
     gpu::check(fftwpp_gpu_memcpy2d(&mine[i*ymax],w,f+i*dy*Z,Z*w,w,dy,1,st),
                "d2h (z=0 plane)");
   DeviceArrays tmp;
@@ -462,7 +497,7 @@ void Convolution3MPI::HermitianSymmetrizeXY(Complex *f)
   }
   const size_t Hx=ceilquotient(Lx,2), Hy=ceilquotient(Ly,2);
   fftwpp::HermitianSymmetrizeXY(Hx,Hy,1,Lx/2,Ly/2,plane.data(),Ly,1);
-  for(size_t i=0; i < Lx; ++i) {
+  for(size_t i=0; i < Lx && dy > 0; ++i) {
     for(size_t j=0; j < dy; ++j) mine[i*ymax+j]=plane[i*Ly+d.y0+j];
     gpu::check(fftwpp_gpu_memcpy2d(f+i*dy*Z,Z*w,&mine[i*ymax],w,w,dy,0,st),
                "h2d (z=0 plane)");

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "convolve.h"
+#include "../../include/fftwpp_gpu.h"
 
 namespace utils {
 
@@ -160,6 +161,7 @@ protected:
   std::vector<void *> peerF;   // [p*B+b]: peer p's x-slab landing buffer b
   std::vector<void *> opened;  // IPC mappings to close
   DeviceArrays devMap;         // row maps (base, stride) per array
+  std::vector<std::vector<fftwpp_gpu_dest> > fwdDests; // [a][peer]
   void setupFused();
   void runFused(Complex **f, size_t offset, double scale);
   void runMPI(Complex **f, size_t offset, double scale);

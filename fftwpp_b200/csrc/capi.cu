@@ -347,6 +347,43 @@ int fftwpp_gpu_backward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
   return rc < 0 ? rc : 0;
 }
 
+int fftwpp_gpu_forward_dests(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
+                             const void *f, const fftwpp_gpu_dest *dests,
+                             int ndest, uint64_t plane0, uint64_t nrows,
+                             uint64_t f_rowstride, void *stream)
+{
+  Plan *pl=(Plan *) plan;
+  int rc=check_range(pl,sb0,nsb);
+  if(rc) return rc;
+  if(!dests || ndest < 1) return FFTWPP_GPU_EINVAL;
+  rc=tma_try_forward(pl,sb0,nsb,1,f,NULL,nrows,f_rowstride,0,
+                     (cudaStream_t) stream,dests,ndest,plane0);
+  if(rc == 0) {
+    set_error("forward_dests: the plan has no TMA-staged forward kernel");
+    return FFTWPP_GPU_EUNSUPPORTED;
+  }
+  return rc < 0 ? rc : 0;
+}
+
+int fftwpp_gpu_backward_dests(fftwpp_gpu_plan *plan, uint64_t sb0,
+                              uint64_t nsb, const void *F,
+                              const fftwpp_gpu_dest *dests, int ndest,
+                              uint64_t plane0, double scale, uint64_t nrows,
+                              uint64_t F_rowstride, void *stream)
+{
+  Plan *pl=(Plan *) plan;
+  int rc=check_range(pl,sb0,nsb);
+  if(rc) return rc;
+  if(!dests || ndest < 1) return FFTWPP_GPU_EINVAL;
+  rc=tma_try_backward(pl,sb0,nsb,1,F,NULL,0,scale,nrows,F_rowstride,0,
+                      (cudaStream_t) stream,dests,ndest,plane0);
+  if(rc == 0) {
+    set_error("backward_dests: the plan has no TMA-staged backward kernel");
+    return FFTWPP_GPU_EUNSUPPORTED;
+  }
+  return rc < 0 ? rc : 0;
+}
+
 int fftwpp_gpu_mapped_supported(fftwpp_gpu_plan *plan, int backward)
 {
   return plan ? fast_mapped_supported((Plan *) plan,backward) : 0;
@@ -393,8 +430,11 @@ int fftwpp_gpu_convolve(fftwpp_gpu_plan *plan, void *const *f, uint32_t A,
     set_error("convolve: multNone needs B <= A");
     return FFTWPP_GPU_EINVAL;
   }
-  int rc=fast_try_convolve(pl,f,A,B,mult,scale,nrows,rowstride,
+  int rc=tmem_try_convolve(pl,f,A,B,mult,scale,nrows,rowstride,
                            (cudaStream_t) stream);
+  if(rc != 0) return rc < 0 ? rc : 0;
+  rc=fast_try_convolve(pl,f,A,B,mult,scale,nrows,rowstride,
+                       (cudaStream_t) stream);
   if(rc != 0) return rc < 0 ? rc : 0;
   return generic_convolve(pl,f,A,B,mult,scale,nrows,rowstride,
                           (cudaStream_t) stream);

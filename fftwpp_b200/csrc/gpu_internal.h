@@ -157,17 +157,26 @@ int fast_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
                       int mult, double scale, uint64_t nrows, uint64_t rs,
                       cudaStream_t st);
 int fast_mapped_supported(Plan *pl, int backward);
+// fused rows with TMEM-parked spectra (tmem_kernels.cu)
+int tmem_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
+                      int mult, double scale, uint64_t nrows, uint64_t rs,
+                      cudaStream_t st);
 
 // TMA-staged strided passes (tma_kernels.cu): tiles move between HBM and
 // shared memory with cp.async.bulk.tensor (tensor maps built per launch),
 // completion on mbarriers.  Same return convention as fast_try_*.
+// dests != NULL: the output rows go to `ndest` destinations (fused exchange,
+// see fftwpp_gpu_forward_dests) instead of F / f.
 int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                     const void *f, void *F, uint64_t nrows, uint64_t frs,
-                    uint64_t Frs, cudaStream_t st);
+                    uint64_t Frs, cudaStream_t st,
+                    const fftwpp_gpu_dest *dests=NULL, int ndest=0,
+                    uint64_t plane0=0);
 int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                      const void *F, void *f, int accumulate, double scale,
                      uint64_t nrows, uint64_t Frs, uint64_t frs,
-                     cudaStream_t st);
+                     cudaStream_t st, const fftwpp_gpu_dest *dests=NULL,
+                     int ndest=0, uint64_t plane0=0);
 
 } // namespace fftwpp_gpu
 

@@ -23,10 +23,11 @@
 // wavefront of a 128-bit access) holds 2 consecutive taus x 4 lanes, i.e. two
 // 64-byte rows; they must fall into different halves of the 128-byte bank
 // window.  Exchanges: positions are padded, p -> p+(p>>3), which gives rows of
-// different parity for every pass.  Staged tiles (the TMA side cannot pad):
-// the tensor maps use the 128-byte swizzle (16-byte chunk index ^= 128-byte
-// line index mod 8), so that rows 8 apart -- what two consecutive taus touch
-// in digit-reversed order -- land in different halves as well.
+// different parity for every pass.  Staged tiles are dense (the TMA side cannot
+// pad), so the digit-reversed accesses of the complex passes (rows 8 apart)
+// keep a 2-way conflict; the real x pass avoids it by ordering its two 128-bit
+// accesses by the parity of tau.  (128-byte swizzled tensor maps were tried
+// for the complex tiles: with a 64-byte inner box they fault on B200.)
 
 #include "regfft.cuh"
 
@@ -128,6 +129,43 @@ __device__ __forceinline__ void fenceAsyncShared()
 }
 
 // ---------------------------------------------------------------------------
+// output destinations
+// ---------------------------------------------------------------------------
+//
+// A pass writes its output rows to one or more destinations, each owning a
+// contiguous range of rows: the local buffer (one destination), or -- fused
+// exchange of the distributed convolutions -- the buffers of the peer GPUs
+// (CUDA-IPC mapped), rows split as the slab decomposition splits them.  The
+// kernels stage their output as a few fixed boxes of rows per tile ("slots":
+// sub-block x box); the host cuts every slot into SEGMENTS, one per owner it
+// overlaps, and encodes one tensor map per segment whose box height is
+// exactly the segment's row count.  A slot is then stored with one bulk
+// tensor store per segment, always inside the tensor bounds (measured: a
+// store whose box starts at a negative coordinate raises an illegal-
+// instruction fault on B200, so nothing relies on clipping).  The peer copies
+// are issued by the TMA unit over NVLink; no thread executes a remote store.
+static const int MAXSEG=24;
+static const int MAXSLOT=8;
+
+struct DestSet {
+  CUtensorMap map[MAXSEG];
+  int srcRow[MAXSEG];   // first row of the segment inside the slot's box
+  int dstRow[MAXSEG];   // row coordinate in the owner's tensor
+  int first[MAXSLOT+1]; // slot s owns segments [first[s],first[s+1])
+  int plane0;
+};
+
+// src: first row of the slot's box in shared memory, rowWords double2 per row
+__device__ __forceinline__ void storeSlot(const DestSet& D, int slot,
+                                          const double2 *src, int rowWords,
+                                          int c0, int plane)
+{
+  for(int i=D.first[slot]; i < D.first[slot+1]; ++i)
+    tmaStore3(&D.map[i],src+D.srcRow[i]*rowWords,c0,D.dstRow[i],
+              D.plane0+plane);
+}
+
+// ---------------------------------------------------------------------------
 // tile geometry
 // ---------------------------------------------------------------------------
 
@@ -163,13 +201,11 @@ __device__ __forceinline__ void threadMap(int& lane, int& tau)
   tau=threadIdx.x/G::T;
 }
 
-// double2 index of (row r, lane) inside a staged tile of 64-byte rows: dense,
-// or with the TMA 128-byte swizzle (tile base 1024-byte aligned)
-template<int T, bool SWZ>
+// double2 index of (row r, lane) inside a staged (dense) tile
+template<int T>
 __device__ __forceinline__ int tileAddr(int r, int lane)
 {
-  if(!SWZ || T != 4) return r*T+lane;
-  return ((r >> 1) << 3)+((((r & 1) << 2)+lane) ^ ((r >> 1) & 7));
+  return r*T+lane;
 }
 
 // 1024-byte aligned start of the dynamic shared memory (swizzle atoms)
@@ -219,10 +255,10 @@ __device__ __forceinline__ void loadZeta(const PlanDev& P,
 // shared memory: [input tile M*T][E0 padded][E1 padded][zeta slots][mbarrier]
 // E0/E1 alternate between sub-blocks: exchange buffer first, then the
 // natural-order output tile that the bulk store reads.
-template<int LG, bool SWZ>
+template<int LG>
 __global__ void __launch_bounds__(256,2)
 tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
-                   const __grid_constant__ CUtensorMap tmOut, PlanDev P,
+                   const __grid_constant__ DestSet out, PlanDev P,
                    const SubBlockDev *__restrict__ sbs, int nsb, int layout,
                    int ntc, long long ntiles, int tabid)
 {
@@ -272,7 +308,7 @@ tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
     double2 xin[8];
 #pragma unroll
     for(int t=0; t < 8; ++t)
-      xin[t]=inS[tileAddr<G::T,SWZ>(tau+G::TPT*t,lane)];
+      xin[t]=inS[tileAddr<G::T>(tau+G::TPT*t,lane)];
     __syncthreads(); // every thread holds its inputs: the stage is free
     if(threadIdx.x == 0 && tile+gridDim.x < ntiles) issueLoad(tile+gridDim.x);
 
@@ -294,7 +330,7 @@ tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
 #pragma unroll
       for(int e=0; e < 8; ++e) {
         const int l=RegFFT<LG>::rev(8*tau+e);
-        buf[tileAddr<G::T,SWZ>(l,lane)]=x[e];
+        buf[tileAddr<G::T>(l,lane)]=x[e];
       }
       fenceAsyncShared();
       __syncthreads();
@@ -303,7 +339,7 @@ tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
         const int r0=(int) (off/P.S);
 #pragma unroll
         for(int b=0; b < G::NBOX; ++b)
-          tmaStore3(&tmOut,buf+b*G::BR*G::T,2*col0,r0+b*G::BR,row);
+          storeSlot(out,isb*G::NBOX+b,buf+b*G::BR*G::T,G::T,2*col0,row);
         tmaCommit();
       }
     }
@@ -319,10 +355,10 @@ tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
 // One stage per sub-block of a tile (NSTAGE >= nsb is required by the host):
 // stage b is refilled with the next tile's sub-block b as soon as every thread
 // has taken its 8 points of the current one.
-template<int LG, int NSTAGE, bool SWZ>
+template<int LG, int NSTAGE>
 __global__ void __launch_bounds__(256,2)
 tma_backward_direct(const __grid_constant__ CUtensorMap tmIn,
-                    const __grid_constant__ CUtensorMap tmOut, PlanDev P,
+                    const __grid_constant__ DestSet out, PlanDev P,
                     const SubBlockDev *__restrict__ sbs, int nsb, int layout,
                     double scale, int ntc, long long ntiles, int tabid)
 {
@@ -384,7 +420,7 @@ tma_backward_direct(const __grid_constant__ CUtensorMap tmIn,
 #pragma unroll
       for(int e=0; e < 8; ++e) {
         const int l=RegFFT<LG>::rev(8*tau+e);
-        x[e]=st[tileAddr<G::T,SWZ>(l,lane)];
+        x[e]=st[tileAddr<G::T>(l,lane)];
       }
       __syncthreads(); // stage consumed (also orders the wait above for E)
       if(threadIdx.x == 0 && tile+gridDim.x < ntiles)
@@ -401,13 +437,13 @@ tma_backward_direct(const __grid_constant__ CUtensorMap tmIn,
     __syncthreads(); // exchange reads done: E becomes the output tile
 #pragma unroll
     for(int t=0; t < 8; ++t)
-      E[tileAddr<G::T,SWZ>(tau+G::TPT*t,lane)]=wscale(racc[t],scale);
+      E[tileAddr<G::T>(tau+G::TPT*t,lane)]=wscale(racc[t],scale);
     fenceAsyncShared();
     __syncthreads();
     if(threadIdx.x == 0) {
 #pragma unroll
       for(int b=0; b < G::NBOX; ++b)
-        tmaStore3(&tmOut,E+b*G::BR*G::T,2*col0,b*G::BR,row);
+        storeSlot(out,b,E+b*G::BR*G::T,G::T,2*col0,row);
       tmaCommit();
     }
   }
@@ -435,8 +471,7 @@ tma_backward_direct(const __grid_constant__ CUtensorMap tmIn,
 template<int LG>
 __global__ void __launch_bounds__(256,2)
 tma_forward_real(const __grid_constant__ CUtensorMap tmIn,
-                 const __grid_constant__ CUtensorMap tmOut,
-                 const __grid_constant__ CUtensorMap tmOut1, PlanDev P,
+                 const __grid_constant__ DestSet out, PlanDev P,
                  const SubBlockDev *__restrict__ sbs, int layout, int ntc,
                  long long ntiles, int tab9, int tab8)
 {
@@ -531,8 +566,8 @@ tma_forward_real(const __grid_constant__ CUtensorMap tmIn,
     fenceAsyncShared();
     __syncthreads();
     if(threadIdx.x == 0) {
-      tmaStore3(&tmOut,Y,2*col0,r0a,row);
-      tmaStore3(&tmOut1,Y+(M/2)*8,2*col0,r0a+M/2,row);
+      storeSlot(out,0,Y,8,2*col0,row);
+      storeSlot(out,1,Y+(M/2)*8,8,2*col0,row);
       tmaCommit();
     }
 
@@ -559,7 +594,7 @@ tma_forward_real(const __grid_constant__ CUtensorMap tmIn,
     fenceAsyncShared();
     __syncthreads();
     if(threadIdx.x == 0) {
-      tmaStore3(&tmOut,X,2*col0,r0b,row);
+      storeSlot(out,2,X,8,2*col0,row);
       tmaCommit();
     }
   }
@@ -751,8 +786,7 @@ EncodeTiledFn encodeTiled()
 // apart, dim2 n2 planes s2 bytes apart; box b0 x b1 x 1.  Out-of-bounds box
 // elements read as zero and are not written.
 bool makeMap(CUtensorMap *map, const void *base, uint64_t n0, uint64_t n1,
-             uint64_t s1, uint64_t n2, uint64_t s2, uint32_t b0, uint32_t b1,
-             bool swizzle)
+             uint64_t s1, uint64_t n2, uint64_t s2, uint32_t b0, uint32_t b1)
 {
   EncodeTiledFn enc=encodeTiled();
   if(!enc) return false;
@@ -768,24 +802,9 @@ bool makeMap(CUtensorMap *map, const void *base, uint64_t n0, uint64_t n1,
   cuuint32_t es[3]={1,1,1};
   CUresult r=enc(map,CU_TENSOR_MAP_DATA_TYPE_FLOAT64,3,(void *) base,dim,
                  stride,box,es,CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 swizzle ? CU_TENSOR_MAP_SWIZZLE_128B :
                  CU_TENSOR_MAP_SWIZZLE_NONE,CU_TENSOR_MAP_L2_PROMOTION_NONE,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
-}
-
-// Staged tiles are dense by default (2-way conflicts remain on the
-// digit-reversed tile accesses).  FFTWPP_TMA_SWIZZLE=1 selects 128-byte
-// swizzled tensor maps -- EXPERIMENTAL: measured to fault on B200 with 64-byte
-// inner boxes (the swizzled box appears to use a 128-byte row pitch).
-bool tmaSwizzle()
-{
-  static int on=-1;
-  if(on < 0) {
-    const char *s=getenv("FFTWPP_TMA_SWIZZLE");
-    on=(s && *s == '1') ? 1 : 0;
-  }
-  return on == 1;
 }
 
 // FFTWPP_NO_TMA_REAL=1: keep the real x pass on the gathering kernels (A/B)
@@ -820,9 +839,12 @@ int allowSmemTma(K kernel, size_t bytes)
   for(size_t i=0; i < done.size(); ++i)
     if(done[i].first == (const void *) kernel && done[i].second == dev)
       return 0;
+  // the budget of two CTAs per SM, whatever this particular launch needs
+  // (the number of residue-twiddle slots varies between launches)
+  (void) bytes;
   cudaError_t e=cudaFuncSetAttribute(kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int) bytes);
+                                     113*1024);
   if(e != cudaSuccess) return cuda_fail(e,"cudaFuncSetAttribute");
   done.push_back(std::make_pair((const void *) kernel,dev));
   return 0;
@@ -906,11 +928,70 @@ bool realEligible(Plan *pl, uint64_t sb0, uint64_t nsb, int layout, int lg,
   return tableId(d,M) >= 0 && tableId(d,M/2) >= 0;
 }
 
+// One store slot of a kernel: `rows` output rows starting at absolute row
+// `row0` (all-layout row of a forward pass, input index j of a backward pass).
+struct Slot {
+  uint64_t row0, rows;
+};
+
+// Cut the slots into per-owner segments and encode their tensor maps.
+// dests == NULL: the dense local layout (rows S words apart, planes
+// planeStride words apart).  rowBytes: bytes of one staged tile row (segment
+// sources must stay 128-byte aligned in shared memory).
+bool makeDests(DestSet *D, const fftwpp_gpu_dest *dests, int ndest,
+               void *local, uint64_t C, uint64_t S, uint64_t rowsMax,
+               uint64_t nplanes, uint64_t planeStride, uint64_t plane0,
+               uint32_t boxCols, size_t rowBytes, const Slot *slots,
+               int nslots)
+{
+  const uint64_t w=sizeof(double2);
+  fftwpp_gpu_dest one;
+  if(!dests) {
+    one.base=local;
+    one.row0=0;
+    one.rows=rowsMax;
+    one.row_stride=S;
+    one.plane_stride=planeStride;
+    dests=&one;
+    ndest=1;
+    plane0=0;
+  }
+  if(ndest < 1 || nslots > MAXSLOT) return false;
+  D->plane0=(int) plane0;
+  const uint64_t planes=plane0+nplanes;
+  int nseg=0;
+  for(int sl=0; sl < nslots; ++sl) {
+    D->first[sl]=nseg;
+    const uint64_t lo=slots[sl].row0, hi=lo+slots[sl].rows;
+    uint64_t covered=0;
+    for(int p=0; p < ndest; ++p) {
+      const fftwpp_gpu_dest& t=dests[p];
+      const uint64_t a=std::max<uint64_t>(lo,t.row0);
+      const uint64_t b=std::min<uint64_t>(hi,t.row0+t.rows);
+      if(a >= b) continue;
+      if(nseg >= MAXSEG) return false;
+      if(((a-lo)*rowBytes) & 127) return false;
+      const uint64_t s2=(planes > 1 ? t.plane_stride : t.row_stride*t.rows)*w;
+      if(!makeMap(&D->map[nseg],t.base,2*C,t.rows,t.row_stride*w,planes,s2,
+                  boxCols,(uint32_t) (b-a)))
+        return false;
+      D->srcRow[nseg]=(int) (a-lo);
+      D->dstRow[nseg]=(int) (a-t.row0);
+      covered += b-a;
+      ++nseg;
+    }
+    if(covered != hi-lo) return false; // every output row needs an owner
+  }
+  for(int sl=nslots; sl <= MAXSLOT; ++sl) D->first[sl]=nseg;
+  return true;
+}
+
 } // namespace
 
 int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                     const void *f, void *F, uint64_t nrows, uint64_t frs,
-                    uint64_t Frs, cudaStream_t st)
+                    uint64_t Frs, cudaStream_t st,
+                    const fftwpp_gpu_dest *dests, int ndest, uint64_t plane0)
 {
   if(tmaDisabled() || !pl->fast) return 0;
   const int lg=pl->fast->log2m;
@@ -919,20 +1000,30 @@ int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   typedef TileGeom<9> G;
   const PlanDev& d=pl->dev;
   const uint64_t w=sizeof(double2);
+  if(dests && !layout) return 0; // destinations own ranges of all-layout rows
   if(realEligible(pl,sb0,nsb,layout,lg,rowsMax) && !tmaRealDisabled()) {
     typedef TileGeom<8> H;
     if(nrows == 0) return 1;
-    if(nrows > 1 && ((frs & 1) || Frs < rowsMax*(uint64_t) d.S)) return 0;
-    CUtensorMap tmIn,tmOut,tmOut1;
+    if(nrows > 1 && ((frs & 1) || (!dests && Frs < rowsMax*(uint64_t) d.S)))
+      return 0;
+    CUtensorMap tmIn;
+    DestSet out;
     if(!makeMap(&tmIn,f,(uint64_t) d.C,(uint64_t) d.Lin,(uint64_t) d.S*8,nrows,
-                (nrows > 1 ? frs : (uint64_t) d.S*d.Lin)*8,8,G::BR,false))
+                (nrows > 1 ? frs : (uint64_t) d.S*d.Lin)*8,8,G::BR))
       return 0;
-    const uint64_t s2=(nrows > 1 ? Frs : (uint64_t) d.S*rowsMax)*w;
-    if(!makeMap(&tmOut,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,s2,16,
-                G::BR,false) ||
-       !makeMap(&tmOut1,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,s2,
-                16,1,false))
-      return 0;
+    {
+      const uint64_t ra=(uint64_t) (pl->hsub[0].off_all/d.S);
+      const uint64_t rb=(uint64_t) (pl->hsub[1].off_all/d.S);
+      const uint64_t ca=(uint64_t) (pl->hsub[0].off_call/d.S);
+      const uint64_t cb=(uint64_t) (pl->hsub[1].off_call/d.S);
+      const Slot slots[3]={{layout ? ra : ca,(uint64_t) G::M/2},
+                           {(layout ? ra : ca)+G::M/2,1},
+                           {layout ? rb : cb,(uint64_t) G::M/2}};
+      if(!makeDests(&out,dests,ndest,F,d.C,d.S,rowsMax,nrows,
+                    nrows > 1 ? Frs : (uint64_t) d.S*rowsMax,plane0,16,128,
+                    slots,3))
+        return 0;
+    }
     const size_t smem=(size_t) (G::TILE+2*G::EPAD+H::ZT)*w+16+1024;
     if(smem > 113*1024) return 0;
     const int ntc=(d.C+7)/8;
@@ -943,42 +1034,50 @@ int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
     if(rc) return rc;
     prof_begin(4*pl->tag+0,st);
     tma_forward_real<9><<<grid,G::NT,smem,st>>>
-      (tmIn,tmOut,tmOut1,pl->dev,pl->dsub,layout,ntc,ntiles,tableId(d,G::M),
+      (tmIn,out,pl->dev,pl->dsub,layout,ntc,ntiles,tableId(d,G::M),
        tableId(d,G::M/2));
     rc=check_launch("tma_forward_real",st);
     return rc ? rc : 1;
   }
   if(!directEligible(pl,sb0,nsb,layout,lg,rowsMax,nz)) return 0;
-  const bool swz=tmaSwizzle();
   if(nrows == 0) return 1;
-  if(nrows > 1 && (Frs < rowsMax*(uint64_t) d.S)) return 0;
-  CUtensorMap tmIn,tmOut;
+  if(nrows > 1 && !dests && Frs < rowsMax*(uint64_t) d.S) return 0;
+  CUtensorMap tmIn;
+  DestSet out;
   // input: C columns, Lin rows S words apart, nrows planes frs words apart
   if(!makeMap(&tmIn,f,2*(uint64_t) d.C,(uint64_t) d.Lin,(uint64_t) d.S*w,nrows,
-              (nrows > 1 ? frs : (uint64_t) d.S*d.Lin)*w,2*G::T,G::BR,swz))
+              (nrows > 1 ? frs : (uint64_t) d.S*d.Lin)*w,2*G::T,G::BR))
     return 0;
-  if(!makeMap(&tmOut,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,
-              (nrows > 1 ? Frs : (uint64_t) d.S*rowsMax)*w,2*G::T,G::BR,swz))
-    return 0;
+  {
+    Slot slots[MAXSLOT];
+    if(nsb*G::NBOX > (uint64_t) MAXSLOT) return 0;
+    int ns=0;
+    for(uint64_t i=sb0; i < sb0+nsb; ++i) {
+      const SubBlockDev& sb=pl->hsub[i];
+      const uint64_t r0=(uint64_t) ((layout ? sb.off_all : sb.off_call)/d.S);
+      for(int b=0; b < G::NBOX; ++b) {
+        slots[ns].row0=r0+b*G::BR;
+        slots[ns].rows=G::BR;
+        ++ns;
+      }
+    }
+    if(!makeDests(&out,dests,ndest,F,d.C,d.S,rowsMax,nrows,
+                  nrows > 1 ? Frs : (uint64_t) d.S*rowsMax,plane0,2*G::T,
+                  G::T*sizeof(double2),slots,ns))
+      return 0;
+  }
   const size_t smem=(size_t) (G::TILE+2*G::EPAD+nz*G::ZT)*w+16+1024;
   if(smem > 113*1024) return 0;
   const int ntc=(d.C+G::T-1)/G::T;
   const long long ntiles=(long long) nrows*ntc;
   const unsigned grid=(unsigned) std::min<long long>(ntiles,
                                                      (long long) smCount()*2);
-  int rc=allowSmemTma(tma_forward_direct<9,true>,smem);
-  if(rc) return rc;
-  rc=allowSmemTma(tma_forward_direct<9,false>,smem);
+  int rc=allowSmemTma(tma_forward_direct<9>,smem);
   if(rc) return rc;
   prof_begin(4*pl->tag+0,st);
-  if(swz)
-    tma_forward_direct<9,true><<<grid,G::NT,smem,st>>>
-      (tmIn,tmOut,pl->dev,pl->dsub+sb0,(int) nsb,layout,ntc,ntiles,
-       tableId(d,G::M));
-  else
-    tma_forward_direct<9,false><<<grid,G::NT,smem,st>>>
-      (tmIn,tmOut,pl->dev,pl->dsub+sb0,(int) nsb,layout,ntc,ntiles,
-       tableId(d,G::M));
+  tma_forward_direct<9><<<grid,G::NT,smem,st>>>
+    (tmIn,out,pl->dev,pl->dsub+sb0,(int) nsb,layout,ntc,ntiles,
+     tableId(d,G::M));
   rc=check_launch("tma_forward_direct",st);
   return rc ? rc : 1;
 }
@@ -986,7 +1085,8 @@ int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
 int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
                      const void *F, void *f, int accumulate, double scale,
                      uint64_t nrows, uint64_t Frs, uint64_t frs,
-                     cudaStream_t st)
+                     cudaStream_t st, const fftwpp_gpu_dest *dests, int ndest,
+                     uint64_t plane0)
 {
   if(tmaDisabled() || !pl->fast || accumulate) return 0;
   const int lg=pl->fast->log2m;
@@ -995,20 +1095,20 @@ int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   typedef TileGeom<9> G;
   const PlanDev& d=pl->dev;
   const uint64_t w=sizeof(double2);
-  if(realEligible(pl,sb0,nsb,layout,lg,rowsMax) && !tmaRealDisabled()) {
+  if(!dests && realEligible(pl,sb0,nsb,layout,lg,rowsMax) &&
+     !tmaRealDisabled()) {
     typedef TileGeom<8> H;
     if(nrows == 0) return 1;
     if(nrows > 1 && ((frs & 1) || Frs < rowsMax*(uint64_t) d.S)) return 0;
     CUtensorMap tmIn,tmIn1,tmOut;
     const uint64_t s2=(nrows > 1 ? Frs : (uint64_t) d.S*rowsMax)*w;
     if(!makeMap(&tmIn,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,s2,16,
-                G::BR,false) ||
+                G::BR) ||
        !makeMap(&tmIn1,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,s2,
-                16,1,false))
+                16,1))
       return 0;
     if(!makeMap(&tmOut,f,(uint64_t) d.C,(uint64_t) d.Lin,(uint64_t) d.S*8,
-                nrows,(nrows > 1 ? frs : (uint64_t) d.S*d.Lin)*8,8,G::BR,
-                false))
+                nrows,(nrows > 1 ? frs : (uint64_t) d.S*d.Lin)*8,8,G::BR))
       return 0;
     const size_t smem=(size_t) ((G::M/2+8)*8+(G::M/2)*8+G::EPAD+H::ZT)*w+32+
       1024;
@@ -1027,37 +1127,43 @@ int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
     return rc ? rc : 1;
   }
   if(!directEligible(pl,sb0,nsb,layout,lg,rowsMax,nz)) return 0;
-  const bool swz=tmaSwizzle();
   if(nsb > 2) return 0; // one staged tile per sub-block, two CTAs per SM
   if(nrows == 0) return 1;
   if(nrows > 1 && (Frs < rowsMax*(uint64_t) d.S)) return 0;
-  CUtensorMap tmIn,tmOut;
+  CUtensorMap tmIn;
+  DestSet out;
   if(!makeMap(&tmIn,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,
-              (nrows > 1 ? Frs : (uint64_t) d.S*rowsMax)*w,2*G::T,G::BR,swz))
+              (nrows > 1 ? Frs : (uint64_t) d.S*rowsMax)*w,2*G::T,G::BR))
     return 0;
-  if(!makeMap(&tmOut,f,2*(uint64_t) d.C,(uint64_t) d.Lin,(uint64_t) d.S*w,
-              nrows,(nrows > 1 ? frs : (uint64_t) d.S*d.Lin)*w,2*G::T,G::BR,
-              swz))
-    return 0;
+  // output rows are the input indices j of the transformed dimension
+  {
+    // the tile holds M rows; rows j >= Lin do not exist in the output
+    Slot slots[G::NBOX];
+    int ns=0;
+    for(int b=0; b < G::NBOX; ++b) {
+      const uint64_t lo=(uint64_t) b*G::BR;
+      const uint64_t hi=std::min<uint64_t>(lo+G::BR,(uint64_t) d.Lin);
+      slots[ns].row0=lo;
+      slots[ns].rows=hi > lo ? hi-lo : 0;
+      ++ns;
+    }
+    if(!makeDests(&out,dests,ndest,f,d.C,d.S,(uint64_t) d.Lin,nrows,
+                  nrows > 1 ? frs : (uint64_t) d.S*d.Lin,plane0,2*G::T,
+                  G::T*sizeof(double2),slots,ns))
+      return 0;
+  }
   const size_t smem=(size_t) (2*G::TILE+G::EPAD+nz*G::ZT)*w+32+1024;
   if(smem > 113*1024) return 0;
   const int ntc=(d.C+G::T-1)/G::T;
   const long long ntiles=(long long) nrows*ntc;
   const unsigned grid=(unsigned) std::min<long long>(ntiles,
                                                      (long long) smCount()*2);
-  int rc=allowSmemTma(tma_backward_direct<9,2,true>,smem);
-  if(rc) return rc;
-  rc=allowSmemTma(tma_backward_direct<9,2,false>,smem);
+  int rc=allowSmemTma(tma_backward_direct<9,2>,smem);
   if(rc) return rc;
   prof_begin(4*pl->tag+1,st);
-  if(swz)
-    tma_backward_direct<9,2,true><<<grid,G::NT,smem,st>>>
-      (tmIn,tmOut,pl->dev,pl->dsub+sb0,(int) nsb,layout,scale,ntc,ntiles,
-       tableId(d,G::M));
-  else
-    tma_backward_direct<9,2,false><<<grid,G::NT,smem,st>>>
-      (tmIn,tmOut,pl->dev,pl->dsub+sb0,(int) nsb,layout,scale,ntc,ntiles,
-       tableId(d,G::M));
+  tma_backward_direct<9,2><<<grid,G::NT,smem,st>>>
+    (tmIn,out,pl->dev,pl->dsub+sb0,(int) nsb,layout,scale,ntc,ntiles,
+     tableId(d,G::M));
   rc=check_launch("tma_backward_direct",st);
   return rc ? rc : 1;
 }

@@ -155,6 +155,21 @@ class SlabConvolution3:
     def convolve_raw(self, arrays):
         return self.convolve(arrays, normalized=False)
 
+    def convolve_async(self, arrays, slot=0, normalized=True):
+        """Pipelined form for PINNED host slabs (fftwpp_b200.pinned_array of
+        local_shape()): returns at once; wait(slot) blocks until the result is
+        back in arrays[0:B].  Collective, two slots."""
+        n = max(self.A, self.B)
+        ptrs = (ctypes.c_void_p * n)(*[_ptr(a) for a in arrays[:n]])
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[slot] = arrays
+        lib.fftwpp_mpiconv3_convolve_async(self._h, ptrs, 1 if normalized else 0, slot)
+
+    def wait(self, slot=0):
+        lib.fftwpp_mpiconv3_wait(self._h, slot)
+        if hasattr(self, "_inflight"):
+            self._inflight.pop(slot, None)
+
     def set_plane_chunk(self, chunk):
         lib.fftwpp_mpiconv3_set_plane_chunk(self._h, int(chunk))
 

@@ -111,6 +111,14 @@ size_t fftwpp_pad_index(void *pad, size_t r, size_t i);
 /* fft->forward(f,F,r) / fft->backward(F,f,r), host or device pointers */
 void fftwpp_pad_forward(void *pad, const double *f, double *F, size_t r);
 void fftwpp_pad_backward(void *pad, const double *F, double *f, size_t r);
+/* All-residues pass (device pointers) with the output rows split among nsplit
+ * owners of ceil-split row ranges inside the same dense buffer: exercises the
+ * destination sets of the fused exchange (fftwpp_gpu_forward_dests) on one
+ * GPU.  Returns 0, or FFTWPP_GPU_EUNSUPPORTED (-5) if the plan has no
+ * TMA-staged kernel. */
+int fftwpp_pad_forward_split(void *pad, const void *f, void *F, size_t nsplit);
+int fftwpp_pad_backward_split(void *pad, const void *F, void *f, size_t nsplit,
+                              double scale);
 
 /* family: 0 complex, 1 centered Hermitian, 2 real (first dimension real).
  * L,M,m,D,I: arrays of `dim` entries in x,y,z order; m[d]==0: chooser.
@@ -187,6 +195,14 @@ void fftwpp_mpiconv3_destroy(void *conv);
 void fftwpp_mpiconv3_split(void *conv, size_t *out);
 void fftwpp_mpiconv3_params(void *conv, int d, size_t *out);
 void fftwpp_mpiconv3_convolve(void *conv, double **f, int normalized);
+/* Pipelined form of fftwpp_mpiconv3_convolve for PINNED HOST slabs (one per
+ * rank, the rank's own y slice): returns at once; fftwpp_mpiconv3_wait(conv,
+ * slot) blocks until the outputs are back in f[0..B).  Two slots; alternate
+ * them to overlap one convolution's PCIe transfers with the other's compute.
+ * Collective: every rank calls it in the same order. */
+void fftwpp_mpiconv3_convolve_async(void *conv, double **f, int normalized,
+                                    int slot);
+void fftwpp_mpiconv3_wait(void *conv, int slot);
 /* byte counts/displacements of exchange `direction` (0 forward, 1 backward);
  * arrays of `size` entries */
 void fftwpp_mpiconv3_exchange_table(void *conv, int direction,

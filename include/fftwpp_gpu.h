@@ -192,6 +192,36 @@ int fftwpp_gpu_backward_mapped(fftwpp_gpu_plan *plan, uint64_t sb0,
                                const int64_t *rowstride, uint64_t plane0,
                                double scale, uint64_t nrows,
                                uint64_t F_rowstride, void *stream);
+/* Fused exchange through the TMA unit (preferred over the row maps above when
+ * the plan's TMA-staged kernels apply; returns FFTWPP_GPU_EUNSUPPORTED
+ * otherwise, and the caller falls back to the *_mapped entry points).  The
+ * output rows of the pass are split among `ndest` destinations, destination p
+ * owning rows [row0,row0+rows): output row r of launch row (plane) i, column c
+ * is stored at
+ *   (word *) base + (r-row0)*row_stride + (plane0+i)*plane_stride + c
+ * where base may point into a PEER GPU's memory (fftwpp_gpu_ipc_open).  Each
+ * destination becomes a tensor map; the kernel's bulk tensor stores
+ * (cp.async.bulk.tensor) are clipped to the owner's rows by the tensor
+ * bounds, so the transposed data crosses NVLink as TMA traffic, not as
+ * per-thread stores.  forward: r = all-residues output row; backward: r =
+ * input index j of the transformed dimension.  Strides in 16-byte words.
+ * Replaces mpitranspose localize1/localize0 (mpi/mpitranspose.h:632-931). */
+typedef struct {
+  void *base;
+  uint64_t row0;
+  uint64_t rows;
+  uint64_t row_stride;
+  uint64_t plane_stride;
+} fftwpp_gpu_dest;
+int fftwpp_gpu_forward_dests(fftwpp_gpu_plan *plan, uint64_t sb0, uint64_t nsb,
+                             const void *f, const fftwpp_gpu_dest *dests,
+                             int ndest, uint64_t plane0, uint64_t nrows,
+                             uint64_t f_rowstride, void *stream);
+int fftwpp_gpu_backward_dests(fftwpp_gpu_plan *plan, uint64_t sb0,
+                              uint64_t nsb, const void *F,
+                              const fftwpp_gpu_dest *dests, int ndest,
+                              uint64_t plane0, double scale, uint64_t nrows,
+                              uint64_t F_rowstride, void *stream);
 /* 1 if the plan's forward (backward != 0: backward) pass can run with a row
  * map, 0 if not (no kernel is launched).  Ranks of a distributed convolution
  * agree on the fused exchange by reducing this predicate. */
