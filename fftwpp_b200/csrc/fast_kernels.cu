@@ -468,307 +468,6 @@ fast_conv_rows_q2(PlanDev P, const SubBlockDev *__restrict__ sbs,
 }
 
 
-// ---------------------------------------------------------------------------
-// One-warp transforms of length 512: 16 points per thread
-// ---------------------------------------------------------------------------
-//
-// The radix-8 kernels above spend most of their shared-memory bandwidth on the
-// two register<->shared exchanges of every 512-point transform.  Here one warp
-// owns a whole transform: 512 = 16 x 16 x 2, two in-register 16-point DFTs
-// with ONE shared-memory exchange between them and the final radix-2 step
-// across lane pairs by shuffles; no CTA-wide or named barriers at all.  The
-// result is in a scrambled order that the fused convolution never needs to
-// undo (both inputs are scrambled alike and adjoint() is the exact adjoint).
-//
-// MEASURED (B200, 512^3 z pass): correct, 40 % fewer shared-memory wavefronts,
-// but SLOWER than fast_conv_rows_pipe -- 8.3 ms with 8 warps/SM (255
-// registers: both inputs' 16 points per thread), 7.7 ms with 12 warps/SM (168
-// registers, small spills) against 6.2 ms for the radix-8 kernel at 16
-// warps/SM.  Latency hiding by resident warps matters more than exchange
-// traffic at these register budgets, so this path stays opt-in
-// (FFTWPP_CONV_WARP=1 or 12) as a reference point for further work.
-
-// omega_32^k, k < 16 (after unrolling k is a compile-time constant)
-__device__ __forceinline__ double2 w32(int k)
-{
-  const double c1=0.98078528040323044913, s1=0.19509032201612826785;
-  const double c2=0.92387953251128675613, s2=0.38268343236508977173;
-  const double c3=0.83146961230254523708, s3=0.55557023301960222474;
-  const double h=0.70710678118654752440;
-  switch(k) {
-    case 0: return make_double2(1.0,0.0);
-    case 1: return make_double2(c1,s1);
-    case 2: return make_double2(c2,s2);
-    case 3: return make_double2(c3,s3);
-    case 4: return make_double2(h,h);
-    case 5: return make_double2(s3,c3);
-    case 6: return make_double2(s2,c2);
-    case 7: return make_double2(s1,c1);
-    case 8: return make_double2(0.0,1.0);
-    case 9: return make_double2(-s1,c1);
-    case 10: return make_double2(-s2,c2);
-    case 11: return make_double2(-s3,c3);
-    case 12: return make_double2(-h,h);
-    case 13: return make_double2(-c3,s3);
-    case 14: return make_double2(-c2,s2);
-    default: return make_double2(-c1,s1);
-  }
-}
-
-// a*omega_16^{SIGN e} for the exponents of a 4x4 decomposition
-template<int SIGN>
-__device__ __forceinline__ double2 mulw16(double2 a, int e)
-{
-  const double h=0.70710678118654752440;
-  if(e == 0) return a;
-  if(e == 4) return rot<SIGN>(a);
-  if(e == 2) { // h (1 + SIGN i)
-    double2 r=rot<SIGN>(a);
-    return make_double2(h*(a.x+r.x),h*(a.y+r.y));
-  }
-  if(e == 6) { // h (-1 + SIGN i)
-    double2 r=rot<SIGN>(a);
-    return make_double2(h*(r.x-a.x),h*(r.y-a.y));
-  }
-  double2 w=w32((2*e) & 15);
-  if(e == 9) w=make_double2(-w32(2).x,-w32(2).y);
-  return SIGN > 0 ? fmul(a,w) : fmulc(a,w);
-}
-
-// 16-point DFT in registers, 4 x 4: input a[t], t=4 t1+t0; output register
-// r=4 k0+k1 holds index k=k0+4 k1 (see K16).
-template<int SIGN>
-__device__ __forceinline__ void dft16_fwd(double2 (&a)[16])
-{
-#pragma unroll
-  for(int t0=0; t0 < 4; ++t0) bfly4<SIGN>(a[t0],a[4+t0],a[8+t0],a[12+t0]);
-#pragma unroll
-  for(int k0=1; k0 < 4; ++k0)
-#pragma unroll
-    for(int t0=1; t0 < 4; ++t0)
-      a[4*k0+t0]=mulw16<SIGN>(a[4*k0+t0],k0*t0);
-#pragma unroll
-  for(int k0=0; k0 < 4; ++k0)
-    bfly4<SIGN>(a[4*k0],a[4*k0+1],a[4*k0+2],a[4*k0+3]);
-}
-
-// the same three steps in reverse order: dft16_rev<-S> is the adjoint of
-// dft16_fwd<S> (input register 4 k0+k1 holds index k0+4 k1, output a[t])
-template<int SIGN>
-__device__ __forceinline__ void dft16_rev(double2 (&a)[16])
-{
-#pragma unroll
-  for(int k0=0; k0 < 4; ++k0)
-    bfly4<SIGN>(a[4*k0],a[4*k0+1],a[4*k0+2],a[4*k0+3]);
-#pragma unroll
-  for(int k0=1; k0 < 4; ++k0)
-#pragma unroll
-    for(int t0=1; t0 < 4; ++t0)
-      a[4*k0+t0]=mulw16<SIGN>(a[4*k0+t0],k0*t0);
-#pragma unroll
-  for(int t0=0; t0 < 4; ++t0) bfly4<SIGN>(a[t0],a[4+t0],a[8+t0],a[12+t0]);
-}
-
-__device__ __forceinline__ double2 shflx1(double2 v)
-{
-  return make_double2(__shfl_xor_sync(0xffffffffu,v.x,1),
-                      __shfl_xor_sync(0xffffffffu,v.y,1));
-}
-
-struct WarpFFT512 {
-  static const int ROW=34;        // padded row of the 16 x 32 exchange buffer
-  static const int BUF=16*ROW;
-  static __host__ __device__ constexpr int K16(int r) {return (r >> 2)+4*(r & 3);}
-
-  // in: x[t]=W[lane+32 t]; twa[k*32+l]=omega_512^{k l}; buf: BUF words owned
-  // by this warp.  out: scrambled spectrum (16 values per lane)
-  static __device__ __forceinline__ void forward(double2 (&x)[16], int lane,
-                                                 const double2 *twa,
-                                                 double2 *buf) {
-    dft16_fwd<1>(x);
-#pragma unroll
-    for(int r=1; r < 16; ++r) x[r]=fmul(x[r],twa[K16(r)*32+lane]);
-    __syncwarp();
-#pragma unroll
-    for(int r=0; r < 16; ++r) buf[K16(r)*ROW+lane]=x[r];
-    __syncwarp();
-    const int g=lane >> 1;
-    const int c=lane & 1;
-#pragma unroll
-    for(int t=0; t < 16; ++t) x[t]=buf[g*ROW+c+2*t];
-    dft16_fwd<1>(x);
-#pragma unroll
-    for(int r=1; r < 16; ++r) {
-      double2 t=fmul(x[r],w32(K16(r)));
-      if(c) x[r]=t;
-    }
-#pragma unroll
-    for(int j=0; j < 8; ++j) {
-      double2 recv=shflx1(c ? x[2*j] : x[2*j+1]);
-      double2 a=c ? recv : x[2*j];
-      double2 b=c ? x[2*j+1] : recv;
-      x[2*j]=a+b;
-      x[2*j+1]=a-b;
-    }
-  }
-
-  // exact adjoint of forward(): out x[t]=w[lane+32 t]
-  static __device__ __forceinline__ void adjoint(double2 (&x)[16], int lane,
-                                                 const double2 *twa,
-                                                 double2 *buf) {
-    const int g=lane >> 1;
-    const int c=lane & 1;
-#pragma unroll
-    for(int j=0; j < 8; ++j) {
-      double2 u=x[2*j]+x[2*j+1];
-      double2 v=x[2*j]-x[2*j+1];
-      double2 recv=shflx1(c ? u : v);
-      x[2*j]=c ? recv : u;
-      x[2*j+1]=c ? v : recv;
-    }
-#pragma unroll
-    for(int r=1; r < 16; ++r) {
-      double2 t=fmulc(x[r],w32(K16(r)));
-      if(c) x[r]=t;
-    }
-    dft16_rev<-1>(x);
-    __syncwarp();
-#pragma unroll
-    for(int t=0; t < 16; ++t) buf[g*ROW+c+2*t]=x[t];
-    __syncwarp();
-#pragma unroll
-    for(int r=0; r < 16; ++r) x[r]=buf[K16(r)*ROW+lane];
-#pragma unroll
-    for(int r=1; r < 16; ++r) x[r]=fmulc(x[r],twa[K16(r)*32+lane]);
-    dft16_rev<-1>(x);
-  }
-};
-
-// Fused rows on one-warp transforms (m=512, L <= m): same software pipeline
-// as fast_conv_rows_pipe, one row per warp, eight independent warps per CTA,
-// one CTA per SM at 255 registers (both inputs' 16 points per thread live in
-// registers around the multiplier).
-template<int WARPS>
-__global__ void __launch_bounds__(32*WARPS,1)
-fast_conv_rows_warp(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
-                    double2 *f0, const double2 *f1, int mult, double scale,
-                    long long nrows, long long rs, int tabid, int zlen)
-{
-  typedef WarpFFT512 FFT;
-  const int NT=32*WARPS;
-  extern __shared__ __align__(16) double2 sm[];
-  double2 *twa=sm;
-  double2 *zs=sm+512;
-  int nz=0;
-  for(int isb=0; isb < nsb; ++isb) nz += sbs[isb].k0 != 0;
-  double2 *bufs=zs+(zlen ? (size_t) nz*zlen : 0);
-  const int warp=threadIdx.x >> 5;
-  const int lane=threadIdx.x & 31;
-  const int L=P.jmax;
-  {
-    const double2 *om=P.tab[tabid].omega;
-    for(int i=threadIdx.x; i < 512; i += NT)
-      twa[i]=__ldg(om+(((i >> 5)*(i & 31)) & 511));
-    if(zlen) {
-      int slot=0;
-      for(int isb=0; isb < nsb; ++isb) {
-        const long long k0=sbs[isb].k0;
-        if(k0 == 0) continue;
-        for(int j=threadIdx.x; j < zlen; j += NT)
-          zs[(size_t) slot*zlen+j]=zeta(P,modN(P,k0,j));
-        ++slot;
-      }
-    }
-  }
-  __syncthreads();
-  double2 *buf=bufs+warp*(FFT::BUF+512);
-  double2 *park=buf+FFT::BUF+lane;
-
-  const long long nw=(long long) gridDim.x*WARPS;
-  long long row=(long long) blockIdx.x*WARPS+warp;
-  if(row >= nrows) return;
-  double2 x[16], y[16];
-  {
-    const double2 *g1=f1+row*rs;
-#pragma unroll
-    for(int t=0; t < 16; ++t) {
-      const int j=lane+32*t;
-      y[t]=j < L ? g1[j] : make_double2(0.0,0.0);
-    }
-  }
-  for(; row < nrows; row += nw) {
-    double2 *g0=f0+row*rs;
-    const double2 *g1=f1+row*rs;
-    const long long nrow=row+nw;
-    const bool more=nrow < nrows;
-    const double2 *n1=f1+(more ? nrow : row)*rs;
-    if(more) {
-      const char *p0=(const char *) (f0+nrow*rs);
-      const char *p1=(const char *) n1;
-      for(int off=lane*128; off < L*16; off += 32*128) {
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
-      }
-    }
-    int slot=0;
-    for(int isb=0; isb < nsb; ++isb) {
-      const long long k0=sbs[isb].k0;
-      const double2 *zrow=zs+(size_t) slot*zlen;
-      if(k0 != 0) ++slot;
-#pragma unroll
-      for(int t=0; t < 16; ++t) {
-        const int j=lane+32*t;
-        x[t]=j < L ? g0[j] : make_double2(0.0,0.0);
-      }
-      if(k0 != 0) {
-#pragma unroll
-        for(int t=0; t < 16; ++t) {
-          const int j=lane+32*t;
-          if(j < L) y[t]=fmul(y[t],zlen ? zrow[j] : zeta(P,modN(P,k0,j)));
-        }
-      }
-      FFT::forward(y,lane,twa,buf);
-      if(k0 != 0) {
-#pragma unroll
-        for(int t=0; t < 16; ++t) {
-          const int j=lane+32*t;
-          if(j < L) x[t]=fmul(x[t],zlen ? zrow[j] : zeta(P,modN(P,k0,j)));
-        }
-      }
-      FFT::forward(x,lane,twa,buf);
-      if(mult == FFTWPP_MULT_BINARY) {
-#pragma unroll
-        for(int t=0; t < 16; ++t) x[t]=fmul(x[t],y[t]);
-      } else {
-#pragma unroll
-        for(int t=0; t < 16; ++t) x[t]=fmulc(x[t],y[t]);
-      }
-      const bool lastsb=isb+1 == nsb;
-      if(!lastsb || more) {
-        const double2 *h1=lastsb ? n1 : g1;
-#pragma unroll
-        for(int t=0; t < 16; ++t) {
-          const int j=lane+32*t;
-          y[t]=j < L ? h1[j] : make_double2(0.0,0.0);
-        }
-      }
-      FFT::adjoint(x,lane,twa,buf);
-#pragma unroll
-      for(int t=0; t < 16; ++t) {
-        const int j=lane+32*t;
-        if(j < L) {
-          double2 v=x[t];
-          if(k0 != 0)
-            v=fmulc(v,zlen ? zrow[j] : zeta(P,modN(P,k0,j)));
-          if(isb > 0) v=v+park[t*32];
-          if(!lastsb) park[t*32]=v;
-          else g0[j]=make_double2(v.x*scale,v.y*scale);
-        }
-      }
-    }
-  }
-}
-
 // Hermitian rows (fftPadHermitian p=2 or explicit; reference forward2/
 // backward2, convolve.cc:4517-4609,4749-4843, with realMultBinary): the input
 // holds the H non-negative modes of a real signal, so every residue's
@@ -1566,111 +1265,54 @@ size_t wordBytes(int kind)
   return kind == FFTWPP_KIND_REAL ? sizeof(double) : sizeof(double2);
 }
 
+// Tuning constants.  They were found with A/B runs on B200 (profiles/README.md)
+// through environment switches; those switches exist only in builds with
+// -DFFTWPP_EXPERIMENT_SWITCHES, the product reads no tuning knobs at run time
+// (FFTWPP_NO_FAST, which forces the generic kernels, is kept for testing).
+#ifdef FFTWPP_EXPERIMENT_SWITCHES
+static int envInt(const char *name, int def)
+{
+  const char *s=getenv(name);
+  return (s && *s) ? atoi(s) : def;
+}
+#define TUNE(name, def) ([]{static int v=envInt(name,def); return v;}())
+#else
+#define TUNE(name, def) (def)
+#endif
+
+// complex lanes per strided tile (64-byte global runs; measured: 2 CTAs/SM of
+// 256 threads beat one CTA with 8 lanes, 17.7 vs 19.0 ms at 512^3)
 int tileLanes()
 {
-  static int T=-1;
-  if(T < 0) {
-    const char *s=getenv("FFTWPP_TILE_LANES");
-    T=s ? atoi(s) : 4;
-    if(T != 2 && T != 4 && T != 8 && T != 16) T=8;
-  }
+  int T=TUNE("FFTWPP_TILE_LANES",4);
+  if(T != 2 && T != 4 && T != 8 && T != 16) T=4;
   return T;
 }
 
-// measured: no gain from ping-pong exchange buffers (the barriers are not
-// the limiter); kept as an experiment switch
-bool pingpongEnabled()
-{
-  static int on=-1;
-  if(on < 0) {
-    const char *s=getenv("FFTWPP_PINGPONG");
-    on=(s && *s && *s != '0') ? 1 : 0;
-  }
-  return on == 1;
-}
+// ping-pong exchange buffers: measured no gain (the barriers are not the limiter)
+bool pingpongEnabled() {return TUNE("FFTWPP_PINGPONG",0) != 0;}
 
 int realLanes()
 {
-  static int T=-1;
-  if(T < 0) {
-    const char *s=getenv("FFTWPP_TILE_LANES_REAL");
-    T=s ? atoi(s) : 2*tileLanes();
-    if(T != 4 && T != 8 && T != 16 && T != 32) T=2*tileLanes();
-  }
+  int T=TUNE("FFTWPP_TILE_LANES_REAL",2*tileLanes());
+  if(T != 4 && T != 8 && T != 16 && T != 32) T=2*tileLanes();
   return T;
 }
 
-bool stageDisabled()
-{
-  static int on=-1;
-  if(on < 0) {
-    const char *s=getenv("FFTWPP_STAGE_REAL");
-    on=(s && *s && *s != '0') ? 1 : 0;
-  }
-  return on == 1;
-}
+// stage the real input tile in shared memory instead of gathering it
+bool stageDisabled() {return TUNE("FFTWPP_STAGE_REAL",0) != 0;}
 
-bool pairDisabled()
-{
-  static int off=-1;
-  if(off < 0) {
-    const char *s=getenv("FFTWPP_NO_PAIR");
-    off=(s && *s && *s != '0') ? 1 : 0;
-  }
-  return off == 1;
-}
+// r2c column pairing off
+bool pairDisabled() {return TUNE("FFTWPP_NO_PAIR",0) != 0;}
 
-// software-pipelined fused convolution (FFTWPP_CONV_PIPE=0 selects the
-// plain kernel for A/B timing)
-bool convPipeEnabled()
-{
-  static int on=-1;
-  if(on < 0) {
-    const char *s=getenv("FFTWPP_CONV_PIPE");
-    on=(s && *s == '0') ? 0 : 1;
-  }
-  return on == 1;
-}
+// software-pipelined fused convolution (0: the plain kernel)
+bool convPipeEnabled() {return TUNE("FFTWPP_CONV_PIPE",1) != 0;}
 
-// FFTWPP_CONV_Q2=0: keep p=1, q=2 rows on the general pipelined kernel (A/B)
-bool convQ2Disabled()
-{
-  static int off=-1;
-  if(off < 0) {
-    const char *s=getenv("FFTWPP_CONV_Q2");
-    off=(s && *s == '0') ? 1 : 0;
-  }
-  return off == 1;
-}
+// p=1, q=2 rows on the specialised straight-line kernel (0: general kernel)
+bool convQ2Disabled() {return TUNE("FFTWPP_CONV_Q2",1) == 0;}
 
-// FFTWPP_THREE_CTAS=0: compile-bound the gathering real forward pass for two
-// CTAs per SM instead of three (A/B switch)
-bool threeCtasEnabled()
-{
-  static int on=-1;
-  if(on < 0) {
-    const char *s=getenv("FFTWPP_THREE_CTAS");
-    on=(s && *s == '0') ? 0 : 1;
-  }
-  return on == 1;
-}
-
-// FFTWPP_CONV_WARP=1: one-warp 512-point transforms in the fused row kernel
-bool convWarpEnabled()
-{
-  static int on=-1;
-  if(on < 0) {
-    const char *s=getenv("FFTWPP_CONV_WARP");
-    on=(s && *s && *s != '0') ? 1 : 0;
-  }
-  return on == 1;
-}
-
-int convWarpCount()
-{
-  const char *s=getenv("FFTWPP_CONV_WARP");
-  return (s && atoi(s) == 12) ? 12 : 8;
-}
+// three CTAs per SM for the gathering real forward pass (+15 %)
+bool threeCtasEnabled() {return TUNE("FFTWPP_THREE_CTAS",1) != 0;}
 
 bool fastDisabled()
 {
@@ -1871,34 +1513,6 @@ int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
   uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) 148*2*4);
   int tabid=0;
   int rc=0;
-  if(NTERM == 1 && lg == 9 && convWarpEnabled() && pl->dev.tab[0].n == 512) {
-    int zl=std::min<int>(pl->dev.jmax,M);
-    size_t zb=(size_t) nz*zl*sizeof(double2);
-    const int W=convWarpCount();
-    size_t sm=(512+(size_t) W*(WarpFFT512::BUF+512))*sizeof(double2);
-    if(sm+zb > SMEM_MAX) {zl=0; zb=0;}
-    sm += zb;
-    uint64_t g=std::min<uint64_t>((nrows+W-1)/W,148);
-    if(W == 12) {
-      rc=allowSmem(fast_conv_rows_warp<12>);
-      if(rc) return rc;
-      prof_begin(4*pl->tag+2,st);
-      fast_conv_rows_warp<12><<<(unsigned) g,32*12,sm,st>>>
-        (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],
-         (const double2 *) f[1],mult,scale,(long long) nrows,(long long) rs,0,
-         zl);
-    } else {
-      rc=allowSmem(fast_conv_rows_warp<8>);
-      if(rc) return rc;
-      prof_begin(4*pl->tag+2,st);
-      fast_conv_rows_warp<8><<<(unsigned) g,32*8,sm,st>>>
-        (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],
-         (const double2 *) f[1],mult,scale,(long long) nrows,(long long) rs,0,
-         zl);
-    }
-    rc=check_launch("fast_conv_rows_warp",st);
-    return rc ? rc : 1;
-  }
   // p=1, q=2, full rows: the straight-line kernel with register twiddles
   if(NTERM == 1 && convPipeEnabled() && !convQ2Disabled() &&
      pl->hsub.size() == 2 && pl->hsub[0].k0 == 0 && pl->hsub[1].k0 != 0 &&

@@ -807,15 +807,21 @@ bool makeMap(CUtensorMap *map, const void *base, uint64_t n0, uint64_t n1,
   return r == CUDA_SUCCESS;
 }
 
-// FFTWPP_NO_TMA_REAL=1: keep the real x pass on the gathering kernels (A/B)
+// FFTWPP_NO_TMA=1 keeps every strided pass on the register-gather kernels of
+// fast_kernels.cu (testing and A/B timing); FFTWPP_NO_TMA_REAL=1 only the real
+// x pass, and only in builds with -DFFTWPP_EXPERIMENT_SWITCHES.
 bool tmaRealDisabled()
 {
+#ifdef FFTWPP_EXPERIMENT_SWITCHES
   static int off=-1;
   if(off < 0) {
     const char *s=getenv("FFTWPP_NO_TMA_REAL");
     off=(s && *s && *s != '0') ? 1 : 0;
   }
   return off == 1;
+#else
+  return false;
+#endif
 }
 
 bool tmaDisabled()

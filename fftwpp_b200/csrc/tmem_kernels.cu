@@ -21,8 +21,13 @@
 // 32x32b = one 32-bit word per thread per column.
 
 #include "regfft.cuh"
+#include "warpfft.cuh"
 
 #include <mutex>
+
+#ifndef FFTWPP_TMEM_DEFAULT
+#define FFTWPP_TMEM_DEFAULT 0
+#endif
 
 namespace fftwpp_gpu {
 
@@ -190,14 +195,136 @@ fast_conv_rows_tm(PlanDev P, const SubBlockDev *__restrict__ sbs,
   if(warp == 0) tmemFree(tmemBase,128);
 }
 
-bool tmemEnabled()
+// One row per warp: 512 = 16 x 16 x 2 transforms (warpfft.cuh), the second
+// input's spectrum and the running sum over residues parked in tensor memory.
+template<int MULT, int WARPS>
+__global__ void __launch_bounds__(32*WARPS,16/WARPS)
+fast_conv_rows_wtm(PlanDev P, const SubBlockDev *__restrict__ sbs,
+                   double2 *f0, const double2 *f1, double scale,
+                   const double2 zstep, long long nrows, long long rs,
+                   int tabid)
 {
-  static int on=-1;
-  if(on < 0) {
-    const char *s=getenv("FFTWPP_CONV_TMEM");
-    on=(s && *s == '0') ? 0 : 1;
+  typedef WarpFFT512 FFT;
+  const int NT=32*WARPS;
+  const int COLS=WARPS <= 4 ? 128 : (WARPS <= 8 ? 256 : 512);
+  extern __shared__ __align__(16) double2 sm[];
+  __shared__ unsigned tmemBase;
+  double2 *twa=sm;          // omega_512^{k l}, k < 16, l < 32
+  double2 *zs=sm+512;       // zeta^{k1 lane}
+  double2 *bufs=zs+32;
+  const int warp=threadIdx.x >> 5;
+  const int lane=threadIdx.x & 31;
+  {
+    const double2 *om=P.tab[tabid].omega;
+    for(int i=threadIdx.x; i < 512; i += NT)
+      twa[i]=__ldg(om+(((i >> 5)*(i & 31)) & 511));
+    for(int i=threadIdx.x; i < 32; i += NT) zs[i]=zeta(P,modN(P,sbs[1].k0,i));
   }
-  return on == 1;
+  if(warp == 0) tmemAlloc(&tmemBase,COLS);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // 128 columns per warp: [spectrum of the second input 64][running sum 64]
+  const unsigned tY=tmemBase+(((unsigned) (32*(warp & 3))) << 16)+(unsigned) ((warp >> 2)*128);
+  const unsigned tA=tY+64;
+  double2 *buf=bufs+warp*FFT::BUF;
+
+  const long long nw=(long long) gridDim.x*WARPS;
+  for(long long row=(long long) blockIdx.x*WARPS+warp; row < nrows; row += nw) {
+    double2 *g0=f0+row*rs+lane;
+    const double2 *g1=f1+row*rs+lane;
+    if(row+nw < nrows) {
+      const char *p0=(const char *) (f0+(row+nw)*rs);
+      const char *p1=(const char *) (f1+(row+nw)*rs);
+      for(int off=lane*128; off < 512*16; off += 32*128) {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
+      }
+    }
+#pragma unroll 1
+    for(int isb=0; isb < 2; ++isb) {
+      const bool hz=isb == 1;
+      double2 x[16];
+#pragma unroll
+      for(int t=0; t < 16; ++t) x[t]=g1[32*t];
+      if(hz) {
+        double2 z=zs[lane];
+#pragma unroll
+        for(int t=0; t < 16; ++t) {
+          x[t]=fmul(x[t],z);
+          if(t < 15) z=fmul(z,zstep);
+        }
+      }
+      FFT::forward(x,lane,twa,buf);
+#pragma unroll
+      for(int h=0; h < 4; ++h) tmemSt4(tY+16*h,x+4*h);
+#pragma unroll
+      for(int t=0; t < 16; ++t) x[t]=g0[32*t];
+      if(hz) {
+        double2 z=zs[lane];
+#pragma unroll
+        for(int t=0; t < 16; ++t) {
+          x[t]=fmul(x[t],z);
+          if(t < 15) z=fmul(z,zstep);
+        }
+      }
+      FFT::forward(x,lane,twa,buf);
+      tmemWaitSt();
+#pragma unroll
+      for(int h=0; h < 4; ++h) {
+        double2 y[4];
+        tmemLd4(tY+16*h,y);
+#pragma unroll
+        for(int t=0; t < 4; ++t)
+          x[4*h+t]=MULT == FFTWPP_MULT_BINARY ? fmul(x[4*h+t],y[t]) : fmulc(x[4*h+t],y[t]);
+      }
+      FFT::adjoint(x,lane,twa,buf);
+      if(!hz) {
+#pragma unroll
+        for(int h=0; h < 4; ++h) tmemSt4(tA+16*h,x+4*h);
+      } else {
+        tmemWaitSt();
+        double2 z=zs[lane];
+#pragma unroll
+        for(int h=0; h < 4; ++h) {
+          double2 a[4];
+          tmemLd4(tA+16*h,a);
+#pragma unroll
+          for(int t=0; t < 4; ++t) {
+            double2 v=fmulc(x[4*h+t],z)+a[t];
+            if(4*h+t < 15) z=fmul(z,zstep);
+            g0[32*(4*h+t)]=make_double2(v.x*scale,v.y*scale);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if(warp == 0) tmemFree(tmemBase,COLS);
+}
+
+// FFTWPP_CONV_TMEM: 0 = off (register/shared-memory kernels of
+// fast_kernels.cu), 1 = radix-8 rows with TMEM parking (24 warps/SM),
+// 2 = one-warp rows with TMEM parking (16 rows in flight per SM)
+int tmemMode()
+{
+  static int mode=-1;
+  if(mode < 0) {
+    const char *s=getenv("FFTWPP_CONV_TMEM");
+    mode=s ? atoi(s) : FFTWPP_TMEM_DEFAULT;
+    if(mode < 0 || mode > 2) mode=0;
+  }
+  return mode;
+}
+
+// zeta_N^{32 k0}: the step between a lane's successive points (one-warp rows)
+double2 zstepw(Plan *pl)
+{
+  const long double ang=2.0L*3.141592653589793238462643383279502884L*
+    (long double) ((pl->hsub[1].k0*32ull) % (unsigned long long) pl->dev.N)/
+    (long double) pl->dev.N;
+  return make_double2((double) cosl(ang),(double) sinl(ang));
 }
 
 template<class K>
@@ -227,7 +354,8 @@ int tmem_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
                       cudaStream_t st)
 {
   FastInfo *fi=pl->fast;
-  if(!tmemEnabled() || !fi || !fi->uniform || fi->nterm != 1) return 0;
+  const int mode=tmemMode();
+  if(mode == 0 || !fi || !fi->uniform || fi->nterm != 1) return 0;
   const PlanDev& d=pl->dev;
   if(fi->log2m != 9 || d.kind != FFTWPP_KIND_COMPLEX || d.C != 1 || d.S != 1)
     return 0;
@@ -254,6 +382,29 @@ int tmem_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
                    (unsigned long long) d.N)/(long double) d.N;
   const double2 zstep=make_double2((double) cosl(ang),(double) sinl(ang));
   int rc=0;
+  if(mode == 2) {
+    const int W=8;
+    const uint64_t gridw=std::min<uint64_t>((nrows+W-1)/W,(uint64_t) sms*2);
+    const size_t smw=(512+32+(size_t) W*WarpFFT512::BUF)*sizeof(double2);
+    if(mult == FFTWPP_MULT_BINARY) {
+      rc=allowSmemT(fast_conv_rows_wtm<FFTWPP_MULT_BINARY,W>,smw);
+      if(rc) return rc;
+      prof_begin(4*pl->tag+2,st);
+      fast_conv_rows_wtm<FFTWPP_MULT_BINARY,W><<<(unsigned) gridw,32*W,smw,st>>>
+        (pl->dev,pl->dsub,(double2 *) f[0],(const double2 *) f[1],scale,
+         zstepw(pl),(long long) nrows,(long long) rs,tabid);
+    } else {
+      rc=allowSmemT(fast_conv_rows_wtm<FFTWPP_MULT_CORRELATION,W>,smw);
+      if(rc) return rc;
+      prof_begin(4*pl->tag+2,st);
+      fast_conv_rows_wtm<FFTWPP_MULT_CORRELATION,W>
+        <<<(unsigned) gridw,32*W,smw,st>>>
+        (pl->dev,pl->dsub,(double2 *) f[0],(const double2 *) f[1],scale,
+         zstepw(pl),(long long) nrows,(long long) rs,tabid);
+    }
+    rc=check_launch("fast_conv_rows_wtm",st);
+    return rc ? rc : 1;
+  }
   if(mult == FFTWPP_MULT_BINARY) {
     rc=allowSmemT(fast_conv_rows_tm<9,FFTWPP_MULT_BINARY>,smem);
     if(rc) return rc;
