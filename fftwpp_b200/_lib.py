@@ -90,6 +90,9 @@ _sig("fftwpp_gpu_comm_create", c_int, c_int, c_int, ctypes.c_char_p, P(c_void_p)
 _sig("fftwpp_gpu_comm_destroy", c_int, c_void_p)
 _sig("fftwpp_mpiconv3_create", c_void_p, c_int, P(c_size_t), P(c_size_t), P(c_size_t),
      P(c_size_t), P(c_long), c_size_t, c_size_t, c_int, c_int, c_int, c_void_p)
+_sig("fftwpp_mpiconv3_create_pencil", c_void_p, c_int, P(c_size_t), P(c_size_t), P(c_size_t),
+     P(c_size_t), P(c_long), c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_int,
+     c_void_p)
 _sig("fftwpp_mpiconv3_destroy", None, c_void_p)
 _sig("fftwpp_mpiconv3_split", None, c_void_p, P(c_size_t))
 _sig("fftwpp_mpiconv3_params", None, c_void_p, c_int, P(c_size_t))

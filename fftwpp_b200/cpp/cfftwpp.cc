@@ -583,7 +583,7 @@ struct MpiConv {
 MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
                      const size_t *m, const size_t *D, const long *I,
                      size_t A, size_t B, int mult, int rank, int size,
-                     void *comm)
+                     void *comm, int rankZ=0, int sizeZ=1, void *commZ=NULL)
 {
   if(family < 0 || family > 2 || (dim == 2 && family == 2)) {
     std::cerr << "distributed convolutions: unsupported dim/family "
@@ -620,9 +620,8 @@ MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
   // deterministic chooser is evaluated for rank 0's slab width on every rank.
   size_t mx=m[0], Dx=D[0];
   long Ix=I[0];
-  if(dim == 2 && family == 1) {
-    std::cerr << "distributed 2-D Hermitian convolutions are not supported "
-              << "(the Hermitian dimension cannot be the split one)"
+  if(sizeZ > 1 && (dim != 3 || family == 1)) {
+    std::cerr << "pencil decomposition: 3-D complex and real families only"
               << std::endl;
     exit(-1);
   }
@@ -634,9 +633,12 @@ MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
     else
       c->app[d]=new Application(A,B,mu,*c->app[d-1],m[d],D[d],Id);
   }
-  size_t rowWords=dim == 2 ? 1 : len[2];
+  // pencil: only the z slice of the second group is local
+  size_t rowWords=dim == 2 ? 1 :
+    std::max<size_t>(utils::localdimension(len[2],rankZ,sizeZ,NULL),1);
   if(mx == 0) {
-    size_t C0=utils::localdimension(len[1],0,size,NULL)*rowWords;
+    size_t C0=utils::localdimension(len[1],0,size,NULL)*
+      (dim == 2 ? 1 : utils::localdimension(len[2],0,sizeZ,NULL));
     fftBase *probe=makePad(kinds[0],L[0],M[0],*c->app[0],C0,C0,0,0,-1);
     mx=probe->m;
     Dx=probe->D;
@@ -648,12 +650,28 @@ MpiConv *makeMpiConv(int dim, int family, const size_t *L, const size_t *M,
     c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],1,0,m[1],D[1],I[1]);
     c->conv2=new Convolution2MPI(c->fft[0],c->fft[1],group);
   } else {
-    size_t Cx=yPlan*len[2];
+    size_t Cx=yPlan*rowWords;
     c->fft[0]=makePad(kinds[0],L[0],M[0],*c->app[0],Cx,Cx,mx,Dx,Ix);
-    c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],len[2],len[2],m[1],D[1],
-                      I[1]);
+    // every rank of the second group must run the y pass with the same
+    // (m,D,I): chosen for the widest z slice (rank 0's)
+    size_t my=m[1], Dy=D[1];
+    long Iy=I[1];
+    if(sizeZ > 1 && my == 0) {
+      size_t z0=utils::localdimension(len[2],0,sizeZ,NULL);
+      fftBase *probe=makePad(kinds[1],L[1],M[1],*c->app[1],z0,z0,0,0,-1);
+      my=probe->m;
+      Dy=probe->D;
+      Iy=probe->inplace;
+      delete probe;
+    }
+    c->fft[1]=makePad(kinds[1],L[1],M[1],*c->app[1],rowWords,rowWords,my,Dy,
+                      Iy);
     c->fft[2]=makePad(kinds[2],L[2],M[2],*c->app[2],1,0,m[2],D[2],I[2]);
-    c->conv3=new Convolution3MPI(c->fft[0],c->fft[1],c->fft[2],group);
+    if(sizeZ > 1) {
+      utils::MPIgroup groupZ(rankZ,sizeZ,commZ);
+      c->conv3=new Convolution3MPI(c->fft[0],c->fft[1],c->fft[2],group,groupZ);
+    } else
+      c->conv3=new Convolution3MPI(c->fft[0],c->fft[1],c->fft[2],group);
   }
   c->A=A;
   c->B=B;
@@ -668,6 +686,21 @@ void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
                              void *comm)
 {
   return makeMpiConv(3,family,L,M,m,D,I,A,B,mult,rank,size,comm);
+}
+
+// Pencil decomposition (forced test / bench mode on one box): y split over
+// the first group, z over the second; arrays are the local pencils
+// Lx x y x z.  out of fftwpp_mpiconv3_split then describes the first group's
+// exchange with Z = the local z extent.
+void *fftwpp_mpiconv3_create_pencil(int family, const size_t *L,
+                                    const size_t *M, const size_t *m,
+                                    const size_t *D, const long *I, size_t A,
+                                    size_t B, int mult, int rankY, int sizeY,
+                                    void *commY, int rankZ, int sizeZ,
+                                    void *commZ)
+{
+  return makeMpiConv(3,family,L,M,m,D,I,A,B,mult,rankY,sizeY,commY,rankZ,sizeZ,
+                     commZ);
 }
 
 void *fftwpp_mpiconv2_create(int family, const size_t *L, const size_t *M,

@@ -32,7 +32,7 @@ Convolution2MPI::Convolution2MPI(fftBase *fftx, fftBase *ffty,
               << std::endl;
     exit(-1);
   }
-  d=split3(fftx->allRows(),ffty->L,1,group);
+  d=split3(fftx->allRows(),ffty->inputLength(),1,group);
   if(fftx->C != std::max<size_t>(d.y,1)) {
     std::cerr << "Convolution2MPI: fftx->C=" << fftx->C
               << " does not match the local slab width " << d.y << std::endl;
@@ -62,14 +62,39 @@ void Convolution2MPI::convolve(Complex **f, size_t offset)
 
 Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
                                  const MPIgroup& group) :
-  Convolution3(fftx,ffty,fftz,NULL,NULL,NULL,true), SlabTranspose(group)
+  Convolution3(fftx,ffty,fftz,NULL,NULL,NULL,true), SlabTranspose(group),
+  inner(NULL)
+{
+  init(group,ffty->S);
+}
+
+Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
+                                 const MPIgroup& group,
+                                 const MPIgroup& groupYZ) :
+  Convolution3(fftx,ffty,fftz,NULL,NULL,NULL,true), SlabTranspose(group),
+  inner(NULL)
+{
+  if(groupYZ.size > 1) {
+    inner=new BatchedTranspose(groupYZ,ffty->allRows(),fftz->inputLength());
+    if(ffty->C != std::max<size_t>(inner->z,1) || ffty->S != ffty->C) {
+      std::cerr << "Convolution3MPI (pencil): ffty must be built for the "
+                << "local z slice (C = S = " << inner->z << ")" << std::endl;
+      exit(-1);
+    }
+  }
+  init(group,ffty->S);
+}
+
+// zlocal: words per y row of the local data (all of z for slabs, the z slice
+// of a pencil)
+void Convolution3MPI::init(const MPIgroup& group, size_t zlocal)
 {
   if(fftx->S != fftx->C) {
     std::cerr << "Convolution3MPI: the local x pass must be contiguous (S == C)"
               << std::endl;
     exit(-1);
   }
-  size_t rowWords=ffty->S;          // words per y row (z extent incl. stride)
+  size_t rowWords=zlocal;          // words per y row (z extent incl. stride)
   d=split3(fftx->allRows(),ffty->L,rowWords,group);
   if(fftx->C != std::max<size_t>(d.y,1)*rowWords) {
     std::cerr << "Convolution3MPI: fftx->C=" << fftx->C
@@ -86,7 +111,7 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
   // the fused exchange needs both strided passes on the power-of-two
   // register kernels (fast_kernels.cu) and the y pass in its direct variant
   auto pow2ok=[](size_t m) {return m >= 64 && m <= 4096 && (m & (m-1)) == 0;};
-  fused=pow2ok(fftx->m) && pow2ok(ffty->m) && ffty->p == 1 &&
+  fused=!inner && pow2ok(fftx->m) && pow2ok(ffty->m) && ffty->p == 1 &&
     ffty->kind() == fftBase::COMPLEX && ffty->C >= 4 && fftx->C >= 4 &&
     fftx->q > 1 && ffty->q > 1 &&
     (fftx->kind() == fftBase::COMPLEX || fftx->kind() == fftBase::REAL) &&
@@ -128,6 +153,135 @@ bool SlabTranspose::agree(bool mine)
 Convolution3MPI::~Convolution3MPI()
 {
   for(size_t i=0; i < opened.size(); ++i) fftwpp_gpu_ipc_close(opened[i]);
+  delete inner;
+}
+
+// ---------------------------------------------------------------------------
+// pencil decomposition
+// ---------------------------------------------------------------------------
+
+BatchedTranspose::BatchedTranspose(const MPIgroup& group, size_t R, size_t Z) :
+  group(group), R(R), Z(Z)
+{
+  r=localdimension(R,group.rank,group.size,&r0);
+  z=localdimension(Z,group.rank,group.size,&z0);
+}
+
+void BatchedTranspose::forward(const void *U, void *V, size_t planes,
+                               DeviceArrays& scratch, void *st)
+{
+  const int P=group.size;
+  const uint64_t w=sizeof(Complex);
+  std::vector<uint64_t> sc(P),sd(P),rc(P),rd(P);
+  uint64_t so=0,ro=0;
+  for(int p=0; p < P; ++p) {
+    size_t pr=localdimension(R,p,P,NULL);
+    size_t pz=localdimension(Z,p,P,NULL);
+    sc[p]=(uint64_t) planes*pr*z*w;   // to p: its rows of my z slice
+    sd[p]=so;
+    so += sc[p];
+    rc[p]=(uint64_t) planes*r*pz*w;   // from p: my rows of its z slice
+    rd[p]=ro;
+    ro += rc[p];
+  }
+  scratch.ensure(2,std::max<uint64_t>(std::max(so,ro),16));
+  char *sendb=(char *) scratch.ptr[0];
+  char *recvb=(char *) scratch.ptr[1];
+  for(int p=0; p < P; ++p) {
+    size_t pr0;
+    size_t pr=localdimension(R,p,P,&pr0);
+    if(pr == 0 || z == 0 || planes == 0) continue;
+    // [plane][row in p's range][k] <- U[plane][pr0+row][k]
+    gpu::check(fftwpp_gpu_copy3(sendb+sd[p],(const Complex *) U+pr0*z,planes,
+                                pr,z,pr*z,z,R*z,z,st),"pack (pencil)");
+  }
+  gpu::check(fftwpp_gpu_comm_alltoallv(group.comm,sendb,sc.data(),sd.data(),
+                                       recvb,rc.data(),rd.data(),st),
+             "all-to-all (pencil, forward)");
+  for(int p=0; p < P; ++p) {
+    size_t pz0;
+    size_t pz=localdimension(Z,p,P,&pz0);
+    if(pz == 0 || r == 0 || planes == 0) continue;
+    gpu::check(fftwpp_gpu_copy3((Complex *) V+pz0,recvb+rd[p],planes,r,pz,r*Z,
+                                Z,r*pz,pz,st),"unpack (pencil)");
+  }
+}
+
+void BatchedTranspose::backward(const void *V, void *U, size_t planes,
+                                DeviceArrays& scratch, void *st)
+{
+  const int P=group.size;
+  const uint64_t w=sizeof(Complex);
+  std::vector<uint64_t> sc(P),sd(P),rc(P),rd(P);
+  uint64_t so=0,ro=0;
+  for(int p=0; p < P; ++p) {
+    size_t pr=localdimension(R,p,P,NULL);
+    size_t pz=localdimension(Z,p,P,NULL);
+    sc[p]=(uint64_t) planes*r*pz*w;   // to p: my rows of its z slice
+    sd[p]=so;
+    so += sc[p];
+    rc[p]=(uint64_t) planes*pr*z*w;   // from p: its rows of my z slice
+    rd[p]=ro;
+    ro += rc[p];
+  }
+  scratch.ensure(2,std::max<uint64_t>(std::max(so,ro),16));
+  char *sendb=(char *) scratch.ptr[0];
+  char *recvb=(char *) scratch.ptr[1];
+  for(int p=0; p < P; ++p) {
+    size_t pz0;
+    size_t pz=localdimension(Z,p,P,&pz0);
+    if(pz == 0 || r == 0 || planes == 0) continue;
+    gpu::check(fftwpp_gpu_copy3(sendb+sd[p],(const Complex *) V+pz0,planes,r,
+                                pz,r*pz,pz,r*Z,Z,st),"pack (pencil)");
+  }
+  gpu::check(fftwpp_gpu_comm_alltoallv(group.comm,sendb,sc.data(),sd.data(),
+                                       recvb,rc.data(),rd.data(),st),
+             "all-to-all (pencil, backward)");
+  for(int p=0; p < P; ++p) {
+    size_t pr0;
+    size_t pr=localdimension(R,p,P,&pr0);
+    if(pr == 0 || z == 0 || planes == 0) continue;
+    gpu::check(fftwpp_gpu_copy3((Complex *) U+pr0*z,recvb+rd[p],planes,pr,z,
+                                R*z,z,pr*z,z,st),"unpack (pencil)");
+  }
+}
+
+// x pass local -> xy exchange over `group` (blocks of the local z slice) ->
+// for the local transformed x rows: y pass local, yz exchange over the second
+// group, z convolutions on rows with all of z, inverse yz exchange, y backward
+// -> inverse xy exchange -> x backward  (reference mpi/mpiconvolve.h:208-305)
+void Convolution3MPI::runPencil(Complex **f, size_t offset, double sc)
+{
+  runSlab(fftx,A,B,devF,f,offset,sc,[this](Complex **T, size_t lo, size_t hi) {
+    size_t N=std::max(A,B);
+    size_t planes=hi-lo;
+    void *st=gpu::stream();
+    size_t zl=inner->z;                 // local z words
+    size_t R=inner->R;                  // transformed y rows
+    size_t planeIn=d.Y*zl;              // words per plane of T
+    const std::vector<ResidueCall>& calls=ffty->calls();
+    size_t nsub=calls.back().sb0+calls.back().nsb;
+    devU.ensure(N,std::max<size_t>(planes*R*zl,1)*sizeof(Complex));
+    devV.ensure(N,std::max<size_t>(planes*inner->r*inner->Z,1)*sizeof(Complex));
+    std::vector<Complex *> V(N);
+    for(size_t a=0; a < N; ++a) V[a]=(Complex *) devV.ptr[a];
+    for(size_t a=0; a < A; ++a) {
+      if(zl > 0)
+        gpu::check(fftwpp_gpu_forward(ffty->plan(),0,nsub,1,
+                                      T[a]+lo*planeIn,devU.ptr[a],planes,
+                                      planeIn,R*zl,st),"forward (pencil y)");
+      inner->forward(devU.ptr[a],devV.ptr[a],planes,devS,st);
+    }
+    if(inner->r > 0)
+      convolveyz[0]->convolvey[0]->convolveRows(V.data(),0,planes*inner->r,inner->Z,1.0);
+    for(size_t b=0; b < B; ++b) {
+      inner->backward(devV.ptr[b],devU.ptr[b],planes,devS,st);
+      if(zl > 0)
+        gpu::check(fftwpp_gpu_backward(ffty->plan(),0,nsub,1,devU.ptr[b],
+                                       T[b]+lo*planeIn,0,1.0,planes,R*zl,
+                                       planeIn,st),"backward (pencil y)");
+    }
+  });
 }
 
 // Sub-range [lo,hi) (relative to the rank's first transformed x row) of
@@ -513,13 +667,15 @@ void Convolution3MPI::HermitianSymmetrizeXY(Complex *f)
 
 void Convolution3MPI::convolveRaw(Complex **f, size_t offset, Indices *)
 {
-  if(fused) runFused(f,offset,1.0);
+  if(inner) runPencil(f,offset,1.0);
+  else if(fused) runFused(f,offset,1.0);
   else runMPI(f,offset,1.0);
 }
 
 void Convolution3MPI::convolve(Complex **f, size_t offset)
 {
-  if(fused) runFused(f,offset,scale);
+  if(inner) runPencil(f,offset,scale);
+  else if(fused) runFused(f,offset,scale);
   else runMPI(f,offset,scale);
 }
 

@@ -9,13 +9,17 @@
  * the local x backward pass.  The adaptive MPI transpose is replaced by one
  * NCCL grouped send/receive per array and direction.
  *
- * Pencil decomposition (a Convolution2MPI nested inside each x row) is only
- * selected by the reference when ranks > Ly (mpigroup.h:33-39); it is not
- * implemented here.  Convolution2MPI itself (2-D data, y split) is.
+ * Pencil decomposition (reference mpi/mpiconvolve.h:208-216: a distributed
+ * y-z convolution nested inside each transformed x row, over a second
+ * communicator; process grid as mpi/mpigroup.h:33-50) is available when a
+ * second group is given: y is split over the first group, z over the second.
+ * The reference only selects it when ranks > Ly, so on one box it is a forced
+ * test / bench mode.  Pencil runs use the NCCL exchanges.
  */
 #ifndef FFTWPP_B200_MPICONVOLVE_H
 #define FFTWPP_B200_MPICONVOLVE_H
 
+#include <algorithm>
 #include <cstdint>
 #include <functional>
 #include <vector>
@@ -60,9 +64,71 @@ public:
   }
 };
 
+// 2-D counterpart (reference mpi/mpigroup.h:69-103): local matrix X x y,
+// transposed x x Y, n = words of the larger of the two.
+class split {
+public:
+  size_t X,Y;
+  size_t x,y;
+  size_t x0,y0;
+  size_t n;
+  split() {}
+  split(size_t X, size_t Y, const MPIgroup& group) : X(X), Y(Y) {
+    x=localdimension(X,group.rank,group.size,&x0);
+    y=localdimension(Y,group.rank,group.size,&y0);
+    n=std::max(X*y,x*Y);
+  }
+};
+
 }
 
 namespace fftwpp {
+
+// Output-buffer decomposition and allocation helpers with the reference's
+// names (mpi/mpiconvolve.h:36-70).  X = l*D transformed rows per residue call,
+// Y / Z = stored input lengths of the inner dimensions.  The buffers these
+// sizes describe are advisory here (device scratch is owned by the
+// convolution objects); outputBuffer returns HOST arrays for callers that
+// pass them to the constructors.
+inline utils::split outputSplit(fftBase *fftx, fftBase *ffty,
+                                const utils::MPIgroup& group)
+{
+  return utils::split(fftx->l*fftx->D,ffty->inputLength(),group);
+}
+
+inline utils::split3 outputSplit(fftBase *fftx, fftBase *ffty, fftBase *fftz,
+                                 const utils::MPIgroup& group)
+{
+  return utils::split3(fftx->l*fftx->D,ffty->inputLength(),
+                       fftz->inputLength(),group);
+}
+
+inline size_t bufferSize(fftBase *fftx, fftBase *ffty,
+                         const utils::MPIgroup& group)
+{
+  return outputSplit(fftx,ffty,group).n;
+}
+
+inline size_t bufferSize(fftBase *fftx, fftBase *ffty, fftBase *fftz,
+                         const utils::MPIgroup& group)
+{
+  utils::split3 d=outputSplit(fftx,ffty,fftz,group);
+  return std::max(d.X*d.y,d.x*d.Y)*d.Z;
+}
+
+inline Complex **outputBuffer(fftBase *fftx, fftBase *ffty,
+                              const utils::MPIgroup& group)
+{
+  return utils::ComplexAlign(std::max(fftx->app.A,fftx->app.B),
+                             bufferSize(fftx,ffty,group));
+}
+
+inline Complex **outputBuffer(fftBase *fftx, fftBase *ffty, fftBase *fftz,
+                              const utils::MPIgroup& group)
+{
+  return utils::ComplexAlign(std::max(fftx->app.A,fftx->app.B),
+                             bufferSize(fftx,ffty,fftz,group));
+}
 
 // The slab exchange shared by the distributed convolutions: global data of
 // X transformed x rows by Y rows of Z words; before the exchange every rank
@@ -104,6 +170,25 @@ protected:
   void transposeBackward(void *T, void *Fx, size_t c, size_t nc, void *st);
 };
 
+// The nested exchange of the pencil decomposition, batched over the local
+// transformed x rows ("planes"): before it every rank of the group holds, for
+// each plane, all R rows of its z slice (planes x R x z); after it its slice
+// of the rows with all of z (planes x r x Z) -- the reference's inner
+// mpitranspose over communicator2 (mpi/mpiconvolve.h:72-179 inside :208-216).
+class BatchedTranspose {
+public:
+  utils::MPIgroup group;
+  size_t R,Z;      // global: rows (transformed y rows), z length
+  size_t r,z;      // local extents
+  size_t r0,z0;
+  BatchedTranspose(const utils::MPIgroup& group, size_t R, size_t Z);
+  // U: planes x R x z  ->  V: planes x r x Z   (device, Complex words)
+  void forward(const void *U, void *V, size_t planes, DeviceArrays& scratch,
+               void *stream);
+  void backward(const void *V, void *U, size_t planes, DeviceArrays& scratch,
+                void *stream);
+};
+
 // Distributed 2-D convolution (reference Convolution2MPI,
 // mpi/mpiconvolve.h:72-179): every rank holds all of x and a slice of y.
 class Convolution2MPI : public Convolution2, public SlabTranspose {
@@ -133,7 +218,13 @@ public:
   // serial case (tests: mpi/tests/hybridconvr3.cc:85-102).
   Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
                   const utils::MPIgroup& group);
+  // Pencil decomposition: y split over `group`, z over `groupYZ`.  fftx is
+  // built for the local pencil (C = S = d.y*z), ffty for the local z slice
+  // (C = S = z), fftz as in the serial case.
+  Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
+                  const utils::MPIgroup& group, const utils::MPIgroup& groupYZ);
   virtual ~Convolution3MPI();
+  bool pencil() const {return inner != NULL;}
 
   // f: device pointers to the local slabs (Lx x d.y x Lz input words each).
   void convolveRaw(Complex **f, size_t offset=0, Indices *indices=NULL);
@@ -156,6 +247,11 @@ public:
   void HermitianSymmetrizeXY(Complex *f);
 
 protected:
+  BatchedTranspose *inner;     // pencil mode: the nested y-z exchange
+  DeviceArrays devU,devV,devS; // pencil mode: y-transformed planes, their
+                               // transposes, pack/unpack scratch
+  void init(const utils::MPIgroup& group, size_t zlocal);
+  void runPencil(Complex **f, size_t offset, double scale);
   bool fusedReady;
   std::vector<void *> peerT;   // [p*N+a]: peer p's transposed buffer a
   std::vector<void *> peerF;   // [p*B+b]: peer p's x-slab landing buffer b

@@ -38,12 +38,46 @@ def _nccl_comm(rank, world):
     return comm
 
 
+def _nccl_subcomm(rank, world, color, key):
+    """NCCL communicator of the ranks sharing `color`, ordered by `key`
+    (the MPI_Comm_split of reference mpi/mpigroup.h:46-48), bootstrapped over
+    torch.distributed: the first rank of every colour creates a unique id,
+    all ids are gathered, every rank joins its colour's communicator.
+    Returns (comm, rank in group, group size)."""
+    import torch
+    import torch.distributed as dist
+    info = torch.tensor([color, key], dtype=torch.int64, device="cuda")
+    allinfo = [torch.zeros_like(info) for _ in range(world)]
+    dist.all_gather(allinfo, info)
+    members = sorted((int(t[1]), r) for r, t in enumerate(allinfo) if int(t[0]) == color)
+    ranks = [r for _, r in members]
+    me = ranks.index(rank)
+    buf = ctypes.create_string_buffer(128)
+    if me == 0:
+        rc = lib.fftwpp_gpu_comm_unique_id(buf)
+        if rc:
+            raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    ids = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(ids, t)
+    raw = bytes(ids[ranks[0]].cpu().tolist())
+    comm = ctypes.c_void_p()
+    rc = lib.fftwpp_gpu_comm_create(me, len(ranks), raw, ctypes.byref(comm))
+    if rc:
+        raise RuntimeError(lib.fftwpp_gpu_last_error().decode())
+    return comm, me, len(ranks)
+
+
 class SlabConvolution2:
     """2-D complex convolution of Lx x Ly data, y split over the ranks
     (reference Convolution2MPI, mpi/mpiconvolve.h:72-179)."""
 
     def __init__(self, Lx, Ly, Mx, My, rank, world, m=None, D=None, I=None, A=2, B=1,
-                 mult=MULT_BINARY, comm="nccl"):
+                 mult=MULT_BINARY, comm="nccl", family=0):
+        """family 0: complex; family 1: centred Hermitian (x centred, y holds
+        the ceil(Ly/2) non-negative modes, split over the ranks; reference
+        mpi/tests/hybridconvh2.cc)."""
+        self.family = family
         self.L, self.M = [Lx, Ly], [Mx, My]
         self.rank, self.world, self.A, self.B = rank, world, A, B
         self._comm = _nccl_comm(rank, world) if comm == "nccl" else ctypes.c_void_p()
@@ -51,7 +85,7 @@ class SlabConvolution2:
         m = arr(*([0] * 2 if m is None else m))
         D = arr(*([0] * 2 if D is None else D))
         I = larr(*([-1] * 2 if I is None else I))
-        self._h = lib.fftwpp_mpiconv2_create(0, arr(*self.L), arr(*self.M), m, D, I,
+        self._h = lib.fftwpp_mpiconv2_create(family, arr(*self.L), arr(*self.M), m, D, I,
                                              A, B, mult, rank, world, self._comm)
         buf = (ctypes.c_size_t * 9)()
         lib.fftwpp_mpiconv2_split(self._h, buf)
@@ -88,16 +122,37 @@ class SlabConvolution3:
     FAMILY_REAL (doubles)."""
 
     def __init__(self, Lx, Ly, Lz, Mx, My, Mz, rank, world, family=FAMILY_REAL,
-                 m=None, D=None, I=None, A=2, B=1, mult=MULT_BINARY, comm="nccl"):
+                 m=None, D=None, I=None, A=2, B=1, mult=MULT_BINARY, comm="nccl", grid=None):
+        """grid=(py,pz) with py*pz == world selects the PENCIL decomposition
+        (y split py ways, z split pz ways; rank = iy*pz + iz; reference
+        mpi/mpigroup.h:33-50, mpi/mpiconvolve.h:208-216): the local arrays are
+        Lx x y x z pencils.  Default: slabs over y."""
         self.L, self.M = [Lx, Ly, Lz], [Mx, My, Mz]
         self.rank, self.world, self.family, self.A, self.B = rank, world, family, A, B
-        self._comm = _nccl_comm(rank, world) if comm == "nccl" else ctypes.c_void_p()
         arr, larr = ctypes.c_size_t * 3, ctypes.c_long * 3
         m = arr(*([0] * 3 if m is None else m))
         D = arr(*([0] * 3 if D is None else D))
         I = larr(*([-1] * 3 if I is None else I))
-        self._h = lib.fftwpp_mpiconv3_create(family, arr(*self.L), arr(*self.M), m, D, I,
-                                             A, B, mult, rank, world, self._comm)
+        self.grid = None
+        self._comm2 = ctypes.c_void_p()
+        self.zsplit = {"z": Lz, "z0": 0}
+        if grid is not None and grid[1] > 1:
+            py, pz = grid
+            if py * pz != world:
+                raise ValueError("grid must multiply to the number of ranks")
+            iy, iz = divmod(rank, pz)
+            self.grid = (py, pz, iy, iz)
+            self._comm, ry, sy = _nccl_subcomm(rank, world, color=iz, key=iy)   # same z slice
+            self._comm2, rz, sz = _nccl_subcomm(rank, world, color=py + iy, key=iz)  # same y slice
+            self._h = lib.fftwpp_mpiconv3_create_pencil(family, arr(*self.L), arr(*self.M), m, D, I,
+                                                        A, B, mult, ry, sy, self._comm, rz, sz,
+                                                        self._comm2)
+            zl, z0 = local_dimension(Lz, rz, sz)
+            self.zsplit = {"z": zl, "z0": z0}
+        else:
+            self._comm = _nccl_comm(rank, world) if comm == "nccl" else ctypes.c_void_p()
+            self._h = lib.fftwpp_mpiconv3_create(family, arr(*self.L), arr(*self.M), m, D, I,
+                                                 A, B, mult, rank, world, self._comm)
         buf = (ctypes.c_size_t * 9)()
         lib.fftwpp_mpiconv3_split(self._h, buf)
         self.split = dict(zip("X Y Z x y z x0 y0 z0".split(), [int(v) for v in buf]))
@@ -117,7 +172,7 @@ class SlabConvolution3:
         return [[int(v) for v in a] for a in t]
 
     def local_shape(self):
-        return (self.L[0], self.split["y"], self.L[2])
+        return (self.L[0], self.split["y"], self.zsplit["z"])
 
     def full_inputs(self, seed=1234, scale_second=None):
         """The globally defined seeded fields (host numpy arrays, every rank
@@ -186,3 +241,6 @@ class SlabConvolution3:
         if self._comm:
             lib.fftwpp_gpu_comm_destroy(self._comm)
             self._comm = ctypes.c_void_p()
+        if self._comm2:
+            lib.fftwpp_gpu_comm_destroy(self._comm2)
+            self._comm2 = ctypes.c_void_p()

@@ -190,6 +190,15 @@ void *fftwpp_mpiconv3_create(int family, const size_t *L, const size_t *M,
                              const size_t *m, const size_t *D, const long *I,
                              size_t A, size_t B, int mult, int rank, int size,
                              void *comm);
+/* Pencil decomposition (reference mpi/mpiconvolve.h:208-216, process grid
+ * mpi/mpigroup.h:33-50): y split over the first communicator, z over the
+ * second; arrays are the local pencils Lx x y x z.  Families 0 and 2. */
+void *fftwpp_mpiconv3_create_pencil(int family, const size_t *L,
+                                    const size_t *M, const size_t *m,
+                                    const size_t *D, const long *I, size_t A,
+                                    size_t B, int mult, int rankY, int sizeY,
+                                    void *commY, int rankZ, int sizeZ,
+                                    void *commZ);
 void fftwpp_mpiconv3_destroy(void *conv);
 /* out = {X,Y,Z,x,y,z,x0,y0,z0} (split3) */
 void fftwpp_mpiconv3_split(void *conv, size_t *out);
@@ -218,8 +227,9 @@ void fftwpp_mpiconv3_symmetrize(void *conv, double *f);
 
 /* ---- distributed 2-D convolution: the reference's Convolution2MPI
  * (mpi/mpiconvolve.h:72-179; driver mpi/tests/hybridconv2.cc).  Arrays are the
- * LOCAL slabs Lx x y of complex words (family 0); L, M, m, D, I have two
- * entries.  Same conventions as the 3-D handle. ---- */
+ * LOCAL slabs Lx x y of complex words (family 0), or Lx x (slice of the
+ * ceil(Ly/2) stored modes) for the centred Hermitian family 1 (reference
+ * mpi/tests/hybridconvh2.cc); L, M, m, D, I have two entries.  Same conventions as the 3-D handle. ---- */
 void *fftwpp_mpiconv2_create(int family, const size_t *L, const size_t *M,
                              const size_t *m, const size_t *D, const long *I,
                              size_t A, size_t B, int mult, int rank, int size,

@@ -92,6 +92,47 @@ def main():
                     want[:, y0:y0 + y, :], np.max(np.abs(want))) and ok
         c.close()
 
+    # pencil decomposition (forced; reference mpi/mpiconvolve.h:208-216): y over
+    # py ranks, z over pz ranks, every admissible grid of this world size
+    grids = [(py, world // py) for py in range(1, world + 1) if world % py == 0 and world // py > 1]
+    for fam, L in ((2, (16, 12, 20)), (0, (8, 10, 6)), (2, (33, 5, 9)), (2, (64, 64, 64))):
+        for (py, pz) in grids:
+            M = [2 * l for l in L]
+            c = dist_conv.SlabConvolution3(*L, *M, rank, world, family=fam, grid=(py, pz))
+            full = [seeded(L, 57 + a, fam == 0) for a in range(2)]
+            y, y0 = c.split["y"], c.split["y0"]
+            z, z0 = c.zsplit["z"], c.zsplit["z0"]
+            f = [torch.from_numpy(np.ascontiguousarray(a[:, y0:y0 + y, z0:z0 + z])).cuda()
+                 for a in full]
+            want = O.conv_real(full[0], full[1]) if fam == 2 else O.conv_complex(full[0], full[1])
+            c.convolve(f)
+            torch.cuda.synchronize()
+            wl = want[:, y0:y0 + y, z0:z0 + z]
+            got = f[0].cpu().numpy() if wl.size else wl
+            ok = report("pencil %dx%d family %d L %s" % (py, pz, fam, L), c, got, wl,
+                        np.max(np.abs(want))) and ok
+            c.close()
+
+    # 2-D centred Hermitian (reference mpi/tests/hybridconvh2.cc): the stored
+    # modes of y (ceil(Ly/2) of them) are split over the ranks
+    for L in ((8, 4 * world), (9, 4 * world + 1), (16, 6 * world - 2)):
+        M = [3 * l // 2 + 1 for l in L]
+        c = dist_conv.SlabConvolution2(*L, *M, rank, world, family=fp.FAMILY_HERMITIAN,
+                                       mult=fp.MULT_REALBINARY)
+        H = (L[1] + 1) // 2
+        full = [seeded((L[0], H), 37 + a, True) for a in range(2)]
+        for a in full:
+            O.symmetrize(L, a)
+        y, y0 = c.split["y"], c.split["y0"]
+        f = [torch.from_numpy(np.ascontiguousarray(a[:, y0:y0 + y])).cuda() for a in full]
+        want = O.conv_hermitian(L, full[0], full[1])
+        c.convolve(f)
+        torch.cuda.synchronize()
+        wl = want[:, y0:y0 + y]
+        got = f[0].cpu().numpy() if wl.size else wl
+        ok = report("2-D Hermitian L %s" % (L,), c, got, wl, np.max(np.abs(want))) and ok
+        c.close()
+
     # 2-D complex (reference Convolution2MPI, mpi/tests/hybridconv2.cc)
     for L in ((16, 4 * world), (33, 3 * (world - 1) + 1), (128, 64 * world)):
         M = [2 * l for l in L]
