@@ -11,6 +11,7 @@ namespace fftwpp {
 
 SlabTranspose::SlabTranspose(const MPIgroup& group) : group(group)
 {
+  emptyZ=false;
   commStream=NULL;
   nchunks=1;
   const char *e=getenv("FFTWPP_MPI_CHUNKS");
@@ -76,6 +77,7 @@ Convolution3MPI::Convolution3MPI(fftBase *fftx, fftBase *ffty, fftBase *fftz,
 {
   if(groupYZ.size > 1) {
     inner=new BatchedTranspose(groupYZ,ffty->allRows(),fftz->inputLength());
+    emptyZ=inner->z == 0; // more ranks than z words: this pencil is empty
     if(ffty->C != std::max<size_t>(inner->z,1) || ffty->S != ffty->C) {
       std::cerr << "Convolution3MPI (pencil): ffty must be built for the "
                 << "local z slice (C = S = " << inner->z << ")" << std::endl;
@@ -385,7 +387,7 @@ void SlabTranspose::runSlab(fftBase *fftx, size_t A, size_t B,
 {
   size_t N=std::max(A,B);
   void *st=gpu::stream();
-  if(d.y > 0 && !gpu::isDevice(f[0])) {
+  if(hasLocal() && !gpu::isDevice(f[0])) {
     std::cerr << "distributed convolutions need device pointers" << std::endl;
     exit(-1);
   }
@@ -420,7 +422,7 @@ void SlabTranspose::runSlab(fftBase *fftx, size_t A, size_t B,
   gpu::check(fftwpp_gpu_stream_wait_event(commStream,evStart),"wait");
 
   for(size_t a=0; a < A; ++a) {
-    if(d.y > 0) // ranks without y rows have no local x pass
+    if(hasLocal()) // ranks without local data have no x pass
       gpu::check(fftwpp_gpu_forward(fftx->plan(),0,nsub,1,f[a]+offset,
                                     devF.ptr[a],1,0,0,st),"forward");
     gpu::check(fftwpp_gpu_event_record(evX[a],st),"event");
@@ -445,7 +447,7 @@ void SlabTranspose::runSlab(fftBase *fftx, size_t A, size_t B,
   }
   gpu::check(fftwpp_gpu_event_record(evB,commStream),"event");
   gpu::check(fftwpp_gpu_stream_wait_event(st,evB),"wait");
-  for(size_t b=0; b < B && d.y > 0; ++b)
+  for(size_t b=0; b < B && hasLocal(); ++b)
     gpu::check(fftwpp_gpu_backward(fftx->plan(),0,nsub,1,devF.ptr[b],
                                    f[b]+offset,0,sc,1,0,0,st),"backward");
 }

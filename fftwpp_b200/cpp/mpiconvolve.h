@@ -151,7 +151,13 @@ public:
   // FFTWPP_MPI_CHUNKS, default 1 (measured: no gain from chunking).
   size_t nchunks;
 
+  // false on ranks that hold no input data (no y rows, or -- pencil -- an
+  // empty z slice): they skip the local x passes and still take part in the
+  // exchanges and the inner sweep
+  bool hasLocal() const {return d.y > 0 && !emptyZ;}
+
 protected:
+  bool emptyZ;
   SlabTranspose(const utils::MPIgroup& group);
   ~SlabTranspose();
   DeviceArrays devT;   // transposed data: x x Y x Z per array
