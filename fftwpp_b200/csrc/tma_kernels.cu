@@ -35,6 +35,10 @@
 
 #include <mutex>
 
+#ifndef FFTWPP_TMA_L2PROMO_DEFAULT
+#define FFTWPP_TMA_L2PROMO_DEFAULT 0
+#endif
+
 namespace fftwpp_gpu {
 
 namespace {
@@ -785,6 +789,22 @@ EncodeTiledFn encodeTiled()
 // 3-D tensor of doubles: dim0 contiguous (n0 doubles), dim1 n1 rows s1 bytes
 // apart, dim2 n2 planes s2 bytes apart; box b0 x b1 x 1.  Out-of-bounds box
 // elements read as zero and are not written.
+// FFTWPP_TMA_L2PROMO (experiment builds): 0 none, 1 64 B, 2 128 B, 3 256 B
+int l2Promotion()
+{
+#ifdef FFTWPP_EXPERIMENT_SWITCHES
+  static int v=-1;
+  if(v < 0) {
+    const char *s=getenv("FFTWPP_TMA_L2PROMO");
+    v=s ? atoi(s) : FFTWPP_TMA_L2PROMO_DEFAULT;
+    if(v < 0 || v > 3) v=0;
+  }
+  return v;
+#else
+  return FFTWPP_TMA_L2PROMO_DEFAULT;
+#endif
+}
+
 bool makeMap(CUtensorMap *map, const void *base, uint64_t n0, uint64_t n1,
              uint64_t s1, uint64_t n2, uint64_t s2, uint32_t b0, uint32_t b1)
 {
@@ -802,7 +822,8 @@ bool makeMap(CUtensorMap *map, const void *base, uint64_t n0, uint64_t n1,
   cuuint32_t es[3]={1,1,1};
   CUresult r=enc(map,CU_TENSOR_MAP_DATA_TYPE_FLOAT64,3,(void *) base,dim,
                  stride,box,es,CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_NONE,CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE,
+                 (CUtensorMapL2promotion) l2Promotion(),
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

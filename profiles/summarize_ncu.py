@@ -61,23 +61,24 @@ def main(path):
         out.append(rec)
         if "fast_conv_rows" in name:
             key = "z convolve"
-        elif "forward_many<3" in name:
+        elif "forward_many<3" in name or "tma_forward_real" in name:
             key = "x forward"
-        elif "backward_many<3" in name:
+        elif "backward_many<3" in name or "tma_backward_real" in name:
             key = "x backward"
-        elif "forward_many<0" in name:
+        elif "forward_many<0" in name or "tma_forward_direct" in name:
             key = "y forward"
-        elif "backward_many<0" in name:
+        elif "backward_many<0" in name or "tma_backward_direct" in name:
             key = "y backward"
         else:
             continue
         b = (scale(d["dram__bytes_read.sum"], unit.get("dram__bytes_read.sum", "byte"))
              + scale(d["dram__bytes_write.sum"], unit.get("dram__bytes_write.sum", "byte")))
         traffic.setdefault(key, []).append(b)
-    with open(os.path.join(HERE, "ncu_r01_summary.json"), "w") as fh:
+    tag = sys.argv[2] if len(sys.argv) > 2 else "r01"
+    with open(os.path.join(HERE, "ncu_%s_summary.json" % tag), "w") as fh:
         json.dump(out, fh, indent=1)
     with open(os.path.join(HERE, "ncu_traffic.json"), "w") as fh:
-        json.dump({"source": "profiles/ncu_r01_summary.json (ncu --set full, one convolution "
+        json.dump({"source": "profiles/ncu_" + tag + "_summary.json (ncu --set full, one convolution "
                              "of bench.py, B200)",
                    "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in traffic.items()}},
                   fh, indent=1)
