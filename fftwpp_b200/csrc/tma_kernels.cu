@@ -173,11 +173,11 @@ __device__ __forceinline__ void storeSlot(const DestSet& D, int slot,
 // tile geometry
 // ---------------------------------------------------------------------------
 
-template<int LG>
+template<int LG, int NTHR=256>
 struct TileGeom {
   static const int M=1 << LG;
   static const int TPT=M/8;               // threads per column
-  static const int NT=256;                // threads per CTA
+  static const int NT=NTHR;               // threads per CTA
   static const int T=NT/TPT;              // columns (lanes) per tile
   static const int BR=M < 256 ? M : 256;  // rows per TMA box
   static const int NBOX=M/BR;
@@ -197,10 +197,10 @@ struct PadLaneLayout {
   __device__ __forceinline__ void sync() const {__syncthreads();}
 };
 
-template<int LG>
+template<int LG, int NTHR>
 __device__ __forceinline__ void threadMap(int& lane, int& tau)
 {
-  typedef TileGeom<LG> G;
+  typedef TileGeom<LG,NTHR> G;
   lane=threadIdx.x % G::T;
   tau=threadIdx.x/G::T;
 }
@@ -277,7 +277,7 @@ tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
   unsigned long long *full=(unsigned long long *) (zt+nz*G::ZT);
 
   int lane,tau;
-  threadMap<LG>(lane,tau);
+  threadMap<LG,256>(lane,tau);
   PadLaneLayout<G::T> lay;
   lay.lane=lane;
   double2 w1[FFT::NR8 > 0 ? FFT::NR8 : 1];
@@ -359,14 +359,14 @@ tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
 // One stage per sub-block of a tile (NSTAGE >= nsb is required by the host):
 // stage b is refilled with the next tile's sub-block b as soon as every thread
 // has taken its 8 points of the current one.
-template<int LG, int NSTAGE>
-__global__ void __launch_bounds__(256,2)
+template<int LG, int NSTAGE, int NTHR>
+__global__ void __launch_bounds__(NTHR,512/NTHR)
 tma_backward_direct(const __grid_constant__ CUtensorMap tmIn,
                     const __grid_constant__ DestSet out, PlanDev P,
                     const SubBlockDev *__restrict__ sbs, int nsb, int layout,
                     double scale, int ntc, long long ntiles, int tabid)
 {
-  typedef TileGeom<LG> G;
+  typedef TileGeom<LG,NTHR> G;
   typedef WFFT<LG> FFT;
   extern __shared__ __align__(128) unsigned char smraw[];
   double2 *inS=(double2 *) alignedSmem(smraw);
@@ -377,7 +377,7 @@ tma_backward_direct(const __grid_constant__ CUtensorMap tmIn,
   unsigned long long *full=(unsigned long long *) (zt+nz*G::ZT);
 
   int lane,tau;
-  threadMap<LG>(lane,tau);
+  threadMap<LG,NTHR>(lane,tau);
   PadLaneLayout<G::T> lay;
   lay.lane=lane;
   double2 w1[FFT::NR8 > 0 ? FFT::NR8 : 1];
@@ -845,6 +845,17 @@ bool tmaRealDisabled()
 #endif
 }
 
+// FFTWPP_TMA_WIDE_REMOTE=0: keep 4-lane tiles for remote destinations (A/B)
+bool wideRemoteTiles()
+{
+  static int on=-1;
+  if(on < 0) {
+    const char *s=getenv("FFTWPP_TMA_WIDE_REMOTE");
+    on=(s && *s == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 bool tmaDisabled()
 {
   static int off=-1;
@@ -856,7 +867,7 @@ bool tmaDisabled()
 }
 
 template<class K>
-int allowSmemTma(K kernel, size_t bytes)
+int allowSmemTma(K kernel, size_t bytes, int budget=113*1024)
 {
   static std::mutex mu;
   static std::vector<std::pair<const void *,int> > done;
@@ -871,7 +882,7 @@ int allowSmemTma(K kernel, size_t bytes)
   (void) bytes;
   cudaError_t e=cudaFuncSetAttribute(kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     113*1024);
+                                     budget);
   if(e != cudaSuccess) return cuda_fail(e,"cudaFuncSetAttribute");
   done.push_back(std::make_pair((const void *) kernel,dev));
   return 0;
@@ -1157,6 +1168,45 @@ int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   if(nsb > 2) return 0; // one staged tile per sub-block, two CTAs per SM
   if(nrows == 0) return 1;
   if(nrows > 1 && (Frs < rowsMax*(uint64_t) d.S)) return 0;
+  // Remote destinations (fused exchange): tiles of 8 lanes, so that the rows
+  // crossing NVLink are 128 bytes long (64-byte rows reach 392 GB/s, 128-byte
+  // rows 633 GB/s at N=8); one CTA of 512 threads per SM -- the pass is then
+  // bound by the link, not by the SM.
+  if(dests && ndest > 1 && d.C >= 8 && wideRemoteTiles()) {
+    typedef TileGeom<9,512> W;
+    CUtensorMap tmInW;
+    DestSet outW;
+    if(makeMap(&tmInW,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,
+               (nrows > 1 ? Frs : (uint64_t) d.S*rowsMax)*w,2*W::T,W::BR)) {
+      Slot slots[W::NBOX];
+      int ns=0;
+      for(int b=0; b < W::NBOX; ++b) {
+        const uint64_t lo=(uint64_t) b*W::BR;
+        const uint64_t hi=std::min<uint64_t>(lo+W::BR,(uint64_t) d.Lin);
+        slots[ns].row0=lo;
+        slots[ns].rows=hi > lo ? hi-lo : 0;
+        ++ns;
+      }
+      const size_t smemW=(size_t) (2*W::TILE+W::EPAD+nz*W::ZT)*w+32+1024;
+      if(smemW <= 227*1024 &&
+         makeDests(&outW,dests,ndest,f,d.C,d.S,(uint64_t) d.Lin,nrows,
+                   nrows > 1 ? frs : (uint64_t) d.S*d.Lin,plane0,2*W::T,
+                   W::T*sizeof(double2),slots,ns)) {
+        const int ntcw=(d.C+W::T-1)/W::T;
+        const long long ntilesw=(long long) nrows*ntcw;
+        const unsigned gridw=(unsigned) std::min<long long>(ntilesw,
+                                                            (long long) smCount());
+        int rcw=allowSmemTma(tma_backward_direct<9,2,512>,smemW,227*1024);
+        if(rcw) return rcw;
+        prof_begin(4*pl->tag+1,st);
+        tma_backward_direct<9,2,512><<<gridw,W::NT,smemW,st>>>
+          (tmInW,outW,pl->dev,pl->dsub+sb0,(int) nsb,layout,scale,ntcw,ntilesw,
+           tableId(d,W::M));
+        rcw=check_launch("tma_backward_direct (wide)",st);
+        return rcw ? rcw : 1;
+      }
+    }
+  }
   CUtensorMap tmIn;
   DestSet out;
   if(!makeMap(&tmIn,F,2*(uint64_t) d.C,rowsMax,(uint64_t) d.S*w,nrows,
@@ -1185,10 +1235,10 @@ int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   const long long ntiles=(long long) nrows*ntc;
   const unsigned grid=(unsigned) std::min<long long>(ntiles,
                                                      (long long) smCount()*2);
-  int rc=allowSmemTma(tma_backward_direct<9,2>,smem);
+  int rc=allowSmemTma(tma_backward_direct<9,2,256>,smem);
   if(rc) return rc;
   prof_begin(4*pl->tag+1,st);
-  tma_backward_direct<9,2><<<grid,G::NT,smem,st>>>
+  tma_backward_direct<9,2,256><<<grid,G::NT,smem,st>>>
     (tmIn,out,pl->dev,pl->dsub+sb0,(int) nsb,layout,scale,ntc,ntiles,
      tableId(d,G::M));
   rc=check_launch("tma_backward_direct",st);
