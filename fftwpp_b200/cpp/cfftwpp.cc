@@ -4,6 +4,7 @@
 // (default M = A*L-A+1 for complex, 3*ceil(L/2)-2*(L%2) for Hermitian).
 #include "convolve.h"
 #include "mpiconvolve.h"
+#include "mpifftw++.h"
 #include "../../include/cfftwpp.h"
 #include "../../include/fftwpp_gpu.h"
 
@@ -832,6 +833,80 @@ void fftwpp_mpiconv3_set_plane_chunk(void *conv, size_t chunk)
 {
   MpiConv *c=(MpiConv *) conv;
   if(c->conv3) c->conv3->convolveyz[0]->planeChunk=chunk;
+}
+
+// ---- distributed FFTs (cpp/mpifftw++.h) ----
+namespace {
+struct MpiFft {
+  int kind,dims;
+  utils::MPIgroup group;
+  fft2dMPI *c;
+  rcfft2dMPI *r;
+  MpiFft(int rank, int size, void *comm) : group(rank,size,comm), c(NULL),
+                                           r(NULL) {}
+  ~MpiFft() {delete c; delete r;}
+  fftMPIBase *base() {return c ? (fftMPIBase *) c : (fftMPIBase *) r;}
+};
+}
+
+void *fftwpp_mpifft_create(int kind, int dims, const size_t *N, int sign,
+                           int rank, int size, void *comm)
+{
+  if((kind != 0 && kind != 1) || (dims != 2 && dims != 3)) {
+    std::cerr << "fftwpp_mpifft_create: kind must be 0 or 1, dims 2 or 3"
+              << std::endl;
+    exit(-1);
+  }
+  MpiFft *h=new MpiFft(rank,size,comm);
+  h->kind=kind;
+  h->dims=dims;
+  if(kind == 0) {
+    if(dims == 2)
+      h->c=new fft2dMPI(utils::split(N[0],N[1],h->group),h->group,sign);
+    else
+      h->c=new fft3dMPI(utils::split3(N[0],N[1],N[2],h->group),h->group,sign);
+  } else {
+    if(dims == 2)
+      h->r=new rcfft2dMPI(utils::split(N[0],N[1],h->group),
+                          utils::split(N[0],N[1]/2+1,h->group),h->group);
+    else
+      h->r=new rcfft3dMPI(utils::split3(N[0],N[1],N[2],h->group),
+                          utils::split3(N[0],N[1],N[2]/2+1,h->group),
+                          h->group);
+  }
+  return h;
+}
+
+void fftwpp_mpifft_destroy(void *fft) {delete (MpiFft *) fft;}
+
+void fftwpp_mpifft_split(void *fft, size_t *out)
+{
+  utils::split3& d=((MpiFft *) fft)->base()->d;
+  out[0]=d.X; out[1]=d.Y; out[2]=d.Z; out[3]=d.x; out[4]=d.y; out[5]=d.z;
+  out[6]=d.x0; out[7]=d.y0; out[8]=d.z0;
+}
+
+size_t fftwpp_mpifft_words(void *fft) {return ((MpiFft *) fft)->base()->n();}
+
+void fftwpp_mpifft_forward(void *fft, void *in, void *out)
+{
+  MpiFft *h=(MpiFft *) fft;
+  if(h->c) h->c->Forward((Complex *) in,(Complex *) out);
+  else h->r->Forward((double *) in,(Complex *) out);
+}
+
+void fftwpp_mpifft_backward(void *fft, void *in, void *out)
+{
+  MpiFft *h=(MpiFft *) fft;
+  if(h->c) h->c->Backward((Complex *) in,(Complex *) out);
+  else h->r->Backward((Complex *) in,(double *) out);
+}
+
+void fftwpp_mpifft_normalize(void *fft, void *f)
+{
+  MpiFft *h=(MpiFft *) fft;
+  if(h->c) h->c->Normalize((Complex *) f);
+  else h->r->Normalize((double *) f);
 }
 
 void fftwpp_set_stream(void *stream) {gpu::setStream(stream);}

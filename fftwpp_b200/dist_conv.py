@@ -244,3 +244,69 @@ class SlabConvolution3:
         if self._comm2:
             lib.fftwpp_gpu_comm_destroy(self._comm2)
             self._comm2 = ctypes.c_void_p()
+
+
+class DistributedFFT:
+    """Distributed 2-D / 3-D FFT, slab decomposition (reference fft2dMPI,
+    fft3dMPI, rcfft2dMPI, rcfft3dMPI; mpi/mpifftw++.h:37-585).
+
+    N: global extents (2 or 3).  real=False: complex transform of the x x Y
+    [x Z] array held as this rank's x rows; forward() leaves the X x y [x Z]
+    array (this rank's y rows), sign -1 by default, unnormalised.  real=True:
+    real input x x Y [x Z]; the complex output halves the last dimension and,
+    in 2-D, splits that halved dimension over the ranks.  Arrays are CUDA
+    tensors; complex ones need `words` complex elements of storage."""
+
+    def __init__(self, N, rank, world, real=False, sign=-1, comm="nccl"):
+        self.N, self.real, self.rank, self.world = list(N), real, rank, world
+        # comm: "nccl" (bootstrap over torch.distributed) or a communicator
+        # handle of fftwpp_gpu_comm_create owned by the caller
+        self._own = comm == "nccl"
+        self._comm = _nccl_comm(rank, world) if self._own else comm
+        dims = len(self.N)
+        arr = ctypes.c_size_t * dims
+        self._h = lib.fftwpp_mpifft_create(1 if real else 0, dims, arr(*self.N), sign, rank,
+                                           world, self._comm)
+        buf = (ctypes.c_size_t * 9)()
+        lib.fftwpp_mpifft_split(self._h, buf)
+        self.split = dict(zip("X Y Z x y z x0 y0 z0".split(), [int(v) for v in buf]))
+        self.words = int(lib.fftwpp_mpifft_words(self._h))
+
+    def _shape(self, a, b):
+        return (a, b) if len(self.N) == 2 else (a, b, self.split["Z"])
+
+    def input_shape(self):
+        """local shape of the x-split COMPLEX data (real=True: of the
+        half-spectrum as Backward leaves it before c2r)"""
+        return self._shape(self.split["x"], self.split["Y"])
+
+    def output_shape(self):
+        return self._shape(self.split["X"], self.split["y"])
+
+    def real_shape(self):
+        x = self.split["x"]
+        return (x, self.N[1]) if len(self.N) == 2 else (x, self.N[1], self.N[2])
+
+    def buffer(self):
+        import torch
+        return torch.zeros(self.words, dtype=torch.complex128, device="cuda")
+
+    def forward(self, src, dst=None):
+        lib.fftwpp_mpifft_forward(self._h, _ptr(src), None if dst is None else _ptr(dst))
+        return src if dst is None else dst
+
+    def backward(self, src, dst=None):
+        lib.fftwpp_mpifft_backward(self._h, _ptr(src), None if dst is None else _ptr(dst))
+        return src if dst is None else dst
+
+    def normalize(self, f):
+        lib.fftwpp_mpifft_normalize(self._h, _ptr(f))
+        return f
+
+    def close(self):
+        if self._h:
+            lib.fftwpp_mpifft_destroy(self._h)
+            self._h = None
+        if self._own and self._comm:
+            lib.fftwpp_gpu_comm_destroy(self._comm)
+            self._comm = ctypes.c_void_p()

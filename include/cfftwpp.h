@@ -244,6 +244,26 @@ void fftwpp_mpiconv2_exchange_table(void *conv, int direction,
                                     unsigned long long *rcount,
                                     unsigned long long *rdispl);
 
+/* ---- distributed FFTs: the reference's fft2dMPI / fft3dMPI / rcfft2dMPI /
+ * rcfft3dMPI (mpi/mpifftw++.h:37-585) on the same exchange and kernels.
+ * kind: 0 complex, 1 real-to-complex.  dims = 2 or 3; N = global extents
+ * (real extents for kind 1).  Complex data: x x Y [x Z] in (this rank's x
+ * rows), X x y [x Z] out (this rank's y rows); kind 1 halves the last
+ * dimension (N/2+1 complex words) and, in 2-D, splits that halved dimension.
+ * Arrays are DEVICE pointers; complex arrays hold fftwpp_mpifft_words() words.
+ * split: X,Y,Z,x,y,z,x0,y0,z0 of the COMPLEX data. ---- */
+void *fftwpp_mpifft_create(int kind, int dims, const size_t *N, int sign,
+                           int rank, int size, void *comm);
+void fftwpp_mpifft_destroy(void *fft);
+void fftwpp_mpifft_split(void *fft, size_t *out);
+size_t fftwpp_mpifft_words(void *fft);
+/* complex: out may be NULL (in place); real: in = double array, out complex */
+void fftwpp_mpifft_forward(void *fft, void *in, void *out);
+/* complex: out may be NULL; real: in complex (overwritten), out doubles */
+void fftwpp_mpifft_backward(void *fft, void *in, void *out);
+/* divide the x x Y [x Z] data (complex kind 0, real kind 1) by the point count */
+void fftwpp_mpifft_normalize(void *fft, void *f);
+
 /* stream used by every launch issued through this API (a cudaStream_t) */
 void fftwpp_set_stream(void *stream);
 

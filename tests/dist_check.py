@@ -146,6 +146,44 @@ def main():
         ok = report("2-D complex L %s" % (L,), c, f[0].cpu().numpy(), want[:, y0:y0 + y],
                     np.max(np.abs(want))) and ok
         c.close()
+
+    # distributed FFTs (reference mpi/mpifftw++.h:37-585; tests mpi/tests/fft2.cc,
+    # fft3.cc, fft2r.cc, fft3r.cc): x-split input, y-split output, against numpy
+    for N in ((16, 12), (4 * world, 4 * world), (9, world - 1), (world + 1, 10), (64, 64),
+              (8, 6, 10), (2 * world, 3 * world, 5), (5, world + 1, 7), (64, 64, 64)):
+        for real in (False, True):
+            if real and N[-1] < 2:
+                continue
+            fft = dist_conv.DistributedFFT(N, rank, world, real=real)
+            sp = fft.split
+            full = seeded(N, 77, not real)
+            x, x0, y, y0 = sp["x"], sp["x0"], sp["y"], sp["y0"]
+            want = np.fft.rfftn(full) if real else np.fft.fftn(full)
+            loc = torch.from_numpy(np.ascontiguousarray(full[x0:x0 + x])).cuda()
+            if real:
+                F = fft.buffer()
+                fft.forward(loc, F)
+            else:
+                F = fft.buffer()
+                F[:loc.numel()] = loc.reshape(-1)
+                fft.forward(F)
+            torch.cuda.synchronize()
+            wl = want[:, y0:y0 + y]
+            got = F.cpu().numpy()[:wl.size].reshape(wl.shape)
+            tag = "%s FFT N %s" % ("real" if real else "complex", N)
+            ok = report(tag + " forward", fft, got, wl, np.max(np.abs(want))) and ok
+            if real:
+                back = torch.zeros_like(loc)
+                fft.backward(F, back)
+                fft.normalize(back)
+                got = back.cpu().numpy()
+            else:
+                fft.backward(F)
+                fft.normalize(F)
+                got = F.cpu().numpy()[:loc.numel()].reshape(loc.shape)
+            torch.cuda.synchronize()
+            ok = report(tag + " round trip", fft, got, full[x0:x0 + x], 1.0) and ok
+            fft.close()
     dist.destroy_process_group()
     if not ok:
         raise SystemExit(1)
