@@ -29,7 +29,9 @@ multiplier *pickMult(int id)
 fftBase *makePad(int kind, size_t L, size_t M, Application &app, size_t C,
                  size_t S, size_t m, size_t D, long I)
 {
-  bool forced=m > 0;
+  // m alone (D == 0): the chooser honours Application.m and picks D itself,
+  // as the reference optimizer does for a partially forced Application
+  bool forced=m > 0 && D > 0;
   switch(kind) {
     case 0:
       return forced ? new fftPad(L,M,app,C,S,m,D,I != 0) :

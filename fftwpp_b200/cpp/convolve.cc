@@ -350,6 +350,14 @@ void fftBase::report(const char *name)
 // (SURVEY Appendix B); the timing is replaced by a cost model of the GPU
 // kernels: work ~ N (log2 m + 2 + p), non-power-of-two m pays the generic
 // mixed-radix kernel, and a candidate must fit the shared-memory tile.
+// FFTWPP_NO_LONG_ROWS=1: rows of 4096 < L <= 8192 take the two-stage (inner)
+// path instead of the tensor-memory row kernel
+static bool longRows()
+{
+  const char *s=getenv("FFTWPP_NO_LONG_ROWS");
+  return !(s && *s && *s != '0');
+}
+
 void fftBase::choose(bool Explicit)
 {
   const bool mForced=app.m >= 1;
@@ -400,10 +408,13 @@ void fftBase::choose(bool Explicit)
     bool inner=qc > 1 && innerEligible(kind(),L,mc,pc,C,S);
     // the fused register kernels (fast_kernels.cu) hold a whole power-of-two
     // row of up to 4096 points (2048 with two input terms) on chip
-    // regardless of the generic kernels' tile estimate
+    // regardless of the generic kernels' tile estimate; p=1, q=2 rows of 8192
+    // points run on the tensor-memory kernel (fast_conv_rows_long)
     bool fusedRow=C == 1 && kind() == COMPLEX && app.A == 2 && app.B == 1 &&
       (app.mult == multBinary || app.mult == multcorrelation) &&
-      ispow2(mc) && mc >= 16 && (pc == 1 ? mc <= 4096 : pc == 2 && mc <= 2048);
+      ispow2(mc) && mc >= 16 &&
+      (pc == 1 ? (mc <= 4096 || (mc == 8192 && qc == 2 && longRows())) :
+       pc == 2 && mc <= 2048);
     if(!mForced && !inner && !fusedRow && lane > smemBytes) continue;
     double N=(double) mc*qc;
     double cost;

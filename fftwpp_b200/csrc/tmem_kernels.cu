@@ -22,6 +22,7 @@
 
 #include "regfft.cuh"
 #include "warpfft.cuh"
+#include "tmem.cuh"
 
 #include <mutex>
 
@@ -32,47 +33,6 @@
 namespace fftwpp_gpu {
 
 namespace {
-
-// ---- tensor memory (TMEM) as thread-private scratch ----
-__device__ __forceinline__ void tmemAlloc(unsigned *slot, int cols)
-{
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-               :: "r"((unsigned) __cvta_generic_to_shared(slot)), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmemFree(unsigned taddr, int cols)
-{
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
-}
-// 4 complex doubles (16 x 32 bit) of this thread's lane at columns [taddr, +16)
-__device__ __forceinline__ void tmemSt4(unsigned taddr, const double2 *v)
-{
-  unsigned r[16];
-#pragma unroll
-  for(int i=0; i < 4; ++i) {
-    r[4*i]=__double2loint(v[i].x); r[4*i+1]=__double2hiint(v[i].x);
-    r[4*i+2]=__double2loint(v[i].y); r[4*i+3]=__double2hiint(v[i].y);
-  }
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-               :: "r"(taddr), "r"(r[0]),"r"(r[1]),"r"(r[2]),"r"(r[3]),"r"(r[4]),"r"(r[5]),"r"(r[6]),"r"(r[7]),
-                  "r"(r[8]),"r"(r[9]),"r"(r[10]),"r"(r[11]),"r"(r[12]),"r"(r[13]),"r"(r[14]),"r"(r[15]) : "memory");
-}
-__device__ __forceinline__ void tmemLd4(unsigned taddr, double2 *v)
-{
-  unsigned r[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]),"=r"(r[1]),"=r"(r[2]),"=r"(r[3]),"=r"(r[4]),"=r"(r[5]),"=r"(r[6]),"=r"(r[7]),
-                 "=r"(r[8]),"=r"(r[9]),"=r"(r[10]),"=r"(r[11]),"=r"(r[12]),"=r"(r[13]),"=r"(r[14]),"=r"(r[15])
-               : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for(int i=0; i < 4; ++i)
-    v[i]=make_double2(__hiloint2double(r[4*i+1],r[4*i]),__hiloint2double(r[4*i+3],r[4*i+2]));
-}
-__device__ __forceinline__ void tmemWaitSt()
-{
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 
 template<int LG, int MULT>
 __global__ void __launch_bounds__(256,3)
@@ -304,6 +264,519 @@ fast_conv_rows_wtm(PlanDev P, const SubBlockDev *__restrict__ sbs,
   if(warp == 0) tmemFree(tmemBase,COLS);
 }
 
+// ---------------------------------------------------------------------------
+// Long rows: m = 8192 (one CTA per row, fully fused)
+// ---------------------------------------------------------------------------
+// A row of 8192 complex words is 128 KB: the padded exchange buffer of ONE
+// transform fills most of an SM's shared memory, so the register/shared-memory
+// kernels stop at m = 4096 and longer rows used to take the two-stage path
+// (three HBM round trips).  Here 512 threads each play two of the 1024
+// "virtual threads" of RegFFT<13> (16 complex points per thread, 64
+// registers), and everything that must survive a transform lives in tensor
+// memory: the transformed second input (64 columns per warp) and the running
+// sum over residues (64 more) -- 4 warps per lane quadrant x 128 columns = all
+// 512 columns, 256 KB, of the SM's TMEM.  HBM traffic is the algorithmic
+// minimum (read both inputs, write one output; the second residue re-reads
+// its inputs from L2).
+//
+// Reference loop being replaced: Convolution::convolveRaw over the residues
+// with multBinary/multcorrelation (convolve.cc:7513-7575,33-110) on
+// fftPad::forward1/backward1 (convolve.cc:849-958,1482-1546), p=1, L <= m.
+template<int LG>
+struct LongRow {
+  typedef RegFFT<LG> RF;
+  static const int M=RF::N;
+  static const int TPT=RF::TPT;     // virtual threads
+  static const int NT=512;          // physical threads
+  static const int VT=TPT/NT;       // virtual threads per physical thread
+  static const int NR8=RF::NR8;
+  static const int BUF=M+M/8;
+
+  // compact table of the radix-8 twiddle bases: pass i holds 2^ls_i entries
+  static __host__ __device__ constexpr int w1Off(int i) {
+    int off=0;
+    for(int k=0; k < i; ++k) off += 1 << (LG-3*(k+1));
+    return off;
+  }
+  static constexpr int W1N=(w1Off(NR8)+15) & ~15;
+
+  static __device__ __forceinline__ int pad(int p) {return p+(p >> 3);}
+
+  // radix-8 twiddle bases: the u=1 block of every pass of the tw8 table
+  static __device__ __forceinline__ void init(const double2 *tw, double2 *w1s,
+                                              int tid)
+  {
+#pragma unroll
+    for(int i=0; i < NR8; ++i) {
+      const int ls=LG-3*(i+1);
+      if(ls > 0)
+        for(int j=tid; j < (1 << ls); j += NT)
+          w1s[w1Off(i)+j]=__ldg(tw+RF::twOff(i)+j);
+    }
+  }
+
+  // x[u] *= w^u (CONJ: conj(w)^u), the powers formed by products as they
+  // are needed so that few of them are live at a time
+  template<bool CONJ>
+  static __device__ __forceinline__ void twiddle(double2 (&x)[8], double2 w1)
+  {
+    if(CONJ) w1.y=-w1.y;
+    x[1]=fmul(x[1],w1);
+    const double2 w2=fmul(w1,w1);
+    x[2]=fmul(x[2],w2);
+    const double2 w3=fmul(w1,w2);
+    x[3]=fmul(x[3],w3);
+    const double2 w4=fmul(w2,w2);
+    x[4]=fmul(x[4],w4);
+    x[5]=fmul(x[5],fmul(w1,w4));
+    x[6]=fmul(x[6],fmul(w3,w3));
+    x[7]=fmul(x[7],fmul(w3,w4));
+  }
+
+  static __device__ __forceinline__ void exchange(double2 (&x)[VT][8], int tid,
+                                                  int lsFrom, int lsTo,
+                                                  double2 *buf)
+  {
+    __syncthreads();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        buf[pad(RF::pos(tid+NT*a,t,lsFrom))]=x[a][t];
+    __syncthreads();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        x[a][t]=buf[pad(RF::pos(tid+NT*a,t,lsTo))];
+  }
+
+  // x[a][t] *= zeta_N^{k0 j} (CONJ: its conjugate), j=tau_a+TPT*t
+  template<bool CONJ>
+  static __device__ __forceinline__ void residue(double2 (&x)[VT][8],
+                                                 const PlanDev& P,
+                                                 long long k0, int tid)
+  {
+    const double2 zst=zeta(P,modN(P,k0,TPT));
+#pragma unroll
+    for(int a=0; a < VT; ++a) {
+      double2 z=zeta(P,modN(P,k0,tid+NT*a));
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        x[a][t]=CONJ ? fmulc(x[a][t],z) : fmul(x[a][t],z);
+        if(t < 7) z=fmul(z,zst);
+      }
+    }
+  }
+
+  // in: x[a][t]=W[tau_a+TPT*t], tau_a=tid+NT*a; out: scrambled position
+  // 8*tau_a+e (RegFFT<LG>::forward with per-array virtual threads)
+  static __device__ __forceinline__ void forward(double2 (&x)[VT][8], int tid,
+                                                 const double2 *w1s,
+                                                 double2 *buf)
+  {
+#pragma unroll
+    for(int i=0; i < NR8; ++i) {
+      const int ls=LG-3*(i+1);
+#pragma unroll
+      for(int a=0; a < VT; ++a) {
+        bfly8<1>(x[a]);
+        if(ls > 0)
+          twiddle<false>(x[a],w1s[w1Off(i)+((tid+NT*a) & ((1 << ls)-1))]);
+      }
+      const int lsNext=(i+1 < NR8) ? LG-3*(i+2) : 0;
+      if(i+1 < NR8 || RF::REM > 0) exchange(x,tid,ls,lsNext,buf);
+    }
+#pragma unroll
+    for(int a=0; a < VT; ++a) {
+      if(RF::REM == 2) {
+        bfly4<1>(x[a][0],x[a][1],x[a][2],x[a][3]);
+        bfly4<1>(x[a][4],x[a][5],x[a][6],x[a][7]);
+      } else if(RF::REM == 1) {
+        bfly2(x[a][0],x[a][1]);
+        bfly2(x[a][2],x[a][3]);
+        bfly2(x[a][4],x[a][5]);
+        bfly2(x[a][6],x[a][7]);
+      }
+    }
+  }
+
+  // exact adjoint of forward()
+  static __device__ __forceinline__ void adjoint(double2 (&x)[VT][8], int tid,
+                                                 const double2 *w1s,
+                                                 double2 *buf)
+  {
+#pragma unroll
+    for(int a=0; a < VT; ++a) {
+      if(RF::REM == 2) {
+        bfly4<-1>(x[a][0],x[a][1],x[a][2],x[a][3]);
+        bfly4<-1>(x[a][4],x[a][5],x[a][6],x[a][7]);
+      } else if(RF::REM == 1) {
+        bfly2(x[a][0],x[a][1]);
+        bfly2(x[a][2],x[a][3]);
+        bfly2(x[a][4],x[a][5]);
+        bfly2(x[a][6],x[a][7]);
+      }
+    }
+#pragma unroll
+    for(int i=NR8-1; i >= 0; --i) {
+      const int ls=LG-3*(i+1);
+      const int lsPrev=(i+1 < NR8) ? LG-3*(i+2) : 0;
+      if(i+1 < NR8 || RF::REM > 0) exchange(x,tid,lsPrev,ls,buf);
+#pragma unroll
+      for(int a=0; a < VT; ++a) {
+        if(ls > 0)
+          twiddle<true>(x[a],w1s[w1Off(i)+((tid+NT*a) & ((1 << ls)-1))]);
+        bfly8<-1>(x[a]);
+      }
+    }
+  }
+};
+
+// 8192 = 16 x 512.  A thread's 16 points are 512 apart, so the first pass is a
+// radix-16 butterfly in registers; ONE CTA-wide exchange then hands each of
+// the 16 warps one 512-point transform (two virtual threads per lane), whose
+// two remaining exchanges need only __syncwarp().  Three exchanges per
+// transform instead of four, and two CTA barriers instead of eight, so the
+// warps drift apart and overlap butterflies with shared-memory traffic.
+// The order of the transformed points differs from RegFFT<13>'s; the fused
+// convolution only multiplies pointwise, so any order shared by forward()
+// and adjoint() serves.
+struct LongRow16 {
+  typedef RegFFT<9> R9;
+  static const int LG=13;
+  static const int M=1 << LG;
+  static const int NT=512;
+  static const int VT=2;
+  static const int TPT=NT*VT;
+  static const int SUB=512;              // points of a warp's transform
+  static const int SUBBUF=SUB+SUB/8;
+  static const int BUF=16*SUBBUF;
+  // tables: w_M^j, j < 512 | w_512^j, j < 64 | w_64^j, j < 8
+  static const int W1N=512+64+16;
+
+  static __device__ __forceinline__ int pad(int p) {return p+(p >> 3);}
+
+  static __device__ __forceinline__ void init(const double2 *tw, double2 *w1s,
+                                              int tid)
+  {
+    // the u=1 block of pass 0 of the tw8 table holds w_M^j, j < M/8
+    for(int j=tid; j < 512; j += NT) w1s[j]=__ldg(tw+j);
+    for(int j=tid; j < 64; j += NT) w1s[512+j]=__ldg(tw+16*j);
+    for(int j=tid; j < 8; j += NT) w1s[576+j]=__ldg(tw+128*j);
+  }
+
+  template<bool CONJ>
+  static __device__ __forceinline__ double2 cm(double2 a, double2 w)
+  {
+    return CONJ ? fmulc(a,w) : fmul(a,w);
+  }
+
+  // x[u] *= w^u (CONJ: conj(w)^u)
+  template<bool CONJ>
+  static __device__ __forceinline__ void twiddle(double2 (&x)[8], double2 w1)
+  {
+    x[1]=cm<CONJ>(x[1],w1);
+    const double2 w2=fmul(w1,w1);
+    x[2]=cm<CONJ>(x[2],w2);
+    const double2 w3=fmul(w1,w2);
+    x[3]=cm<CONJ>(x[3],w3);
+    const double2 w4=fmul(w2,w2);
+    x[4]=cm<CONJ>(x[4],w4);
+    x[5]=cm<CONJ>(x[5],fmul(w1,w4));
+    x[6]=cm<CONJ>(x[6],fmul(w3,w3));
+    x[7]=cm<CONJ>(x[7],fmul(w3,w4));
+  }
+
+  // y_k *= w^k (CONJ: conj), k = k8+8a over x[a][k8]
+  template<bool CONJ>
+  static __device__ __forceinline__ void twiddle16(double2 (&x)[VT][8],
+                                                   double2 w1)
+  {
+    const double2 w2=fmul(w1,w1);
+    const double2 w4=fmul(w2,w2);
+    const double2 w8=fmul(w4,w4);
+    x[1][0]=cm<CONJ>(x[1][0],w8);
+    x[0][1]=cm<CONJ>(x[0][1],w1);
+    x[1][1]=cm<CONJ>(x[1][1],fmul(w1,w8));
+    x[0][2]=cm<CONJ>(x[0][2],w2);
+    x[1][2]=cm<CONJ>(x[1][2],fmul(w2,w8));
+    const double2 w3=fmul(w1,w2);
+    x[0][3]=cm<CONJ>(x[0][3],w3);
+    x[1][3]=cm<CONJ>(x[1][3],fmul(w3,w8));
+    x[0][4]=cm<CONJ>(x[0][4],w4);
+    x[1][4]=cm<CONJ>(x[1][4],fmul(w4,w8));
+    const double2 w5=fmul(w1,w4);
+    x[0][5]=cm<CONJ>(x[0][5],w5);
+    x[1][5]=cm<CONJ>(x[1][5],fmul(w5,w8));
+    const double2 w6=fmul(w3,w3);
+    x[0][6]=cm<CONJ>(x[0][6],w6);
+    x[1][6]=cm<CONJ>(x[1][6],fmul(w6,w8));
+    const double2 w7=fmul(w3,w4);
+    x[0][7]=cm<CONJ>(x[0][7],w7);
+    x[1][7]=cm<CONJ>(x[1][7],fmul(w7,w8));
+  }
+
+  // x[1][k] *= exp(2 pi i k/16) (CONJ: its conjugate)
+  template<bool CONJ>
+  static __device__ __forceinline__ void rot16(double2 (&z)[8])
+  {
+    const double c=0.92387953251128675613; // cos(pi/8)
+    const double s=0.38268343236508977173; // sin(pi/8)
+    const double h=0.70710678118654752440;
+    z[1]=cm<CONJ>(z[1],make_double2(c,s));
+    z[2]=cm<CONJ>(z[2],make_double2(h,h));
+    z[3]=cm<CONJ>(z[3],make_double2(s,c));
+    z[4]=CONJ ? rot<-1>(z[4]) : rot<1>(z[4]);
+    z[5]=cm<CONJ>(z[5],make_double2(-s,c));
+    z[6]=cm<CONJ>(z[6],make_double2(-h,h));
+    z[7]=cm<CONJ>(z[7],make_double2(-c,s));
+  }
+
+  // exchange inside a warp's 512-point region
+  static __device__ __forceinline__ void warpExchange(double2 (&x)[VT][8],
+                                                      int lane, int lsFrom,
+                                                      int lsTo, double2 *reg)
+  {
+    __syncwarp();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        reg[pad(R9::pos(lane+32*a,t,lsFrom))]=x[a][t];
+    __syncwarp();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        x[a][t]=reg[pad(R9::pos(lane+32*a,t,lsTo))];
+  }
+
+  // in: x[a][t]=W[tid+512*(a+2t)]; out: some fixed order of the transform
+  static __device__ __forceinline__ void forward(double2 (&x)[VT][8], int tid,
+                                                 const double2 *w1s,
+                                                 double2 *buf)
+  {
+    const int warp=tid >> 5, lane=tid & 31;
+    double2 *reg=buf+warp*SUBBUF;
+    // radix 16 over s=a+2t: y_k = sum_s x_s w_16^{sk}, k=k8+8a
+    bfly8<1>(x[0]);
+    bfly8<1>(x[1]);
+    rot16<false>(x[1]);
+#pragma unroll
+    for(int k=0; k < 8; ++k) bfly2(x[0][k],x[1][k]);
+    twiddle16<false>(x,w1s[tid]);
+    // y_k[tid] -> transform k, column tid
+    __syncthreads();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int k=0; k < 8; ++k)
+        buf[(k+8*a)*SUBBUF+pad(tid)]=x[a][k];
+    __syncthreads();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        x[a][t]=reg[pad(lane+32*a+64*t)];
+    // 512 points per warp: RegFFT<9> with two virtual threads per lane
+#pragma unroll
+    for(int i=0; i < 3; ++i) {
+      const int ls=9-3*(i+1);
+#pragma unroll
+      for(int a=0; a < VT; ++a) {
+        bfly8<1>(x[a]);
+        if(ls > 0)
+          twiddle<false>(x[a],w1s[(i == 0 ? 512 : 576)+
+                                  ((lane+32*a) & ((1 << ls)-1))]);
+      }
+      if(i < 2) warpExchange(x,lane,ls,ls-3,reg);
+    }
+  }
+
+  // exact adjoint of forward()
+  static __device__ __forceinline__ void adjoint(double2 (&x)[VT][8], int tid,
+                                                 const double2 *w1s,
+                                                 double2 *buf)
+  {
+    const int warp=tid >> 5, lane=tid & 31;
+    double2 *reg=buf+warp*SUBBUF;
+#pragma unroll
+    for(int i=2; i >= 0; --i) {
+      const int ls=9-3*(i+1);
+      if(i < 2) warpExchange(x,lane,ls-3,ls,reg);
+#pragma unroll
+      for(int a=0; a < VT; ++a) {
+        if(ls > 0)
+          twiddle<true>(x[a],w1s[(i == 0 ? 512 : 576)+
+                                 ((lane+32*a) & ((1 << ls)-1))]);
+        bfly8<-1>(x[a]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int t=0; t < 8; ++t)
+        reg[pad(lane+32*a+64*t)]=x[a][t];
+    __syncthreads();
+#pragma unroll
+    for(int a=0; a < VT; ++a)
+#pragma unroll
+      for(int k=0; k < 8; ++k)
+        x[a][k]=buf[(k+8*a)*SUBBUF+pad(tid)];
+    twiddle16<true>(x,w1s[tid]);
+#pragma unroll
+    for(int k=0; k < 8; ++k) bfly2(x[0][k],x[1][k]);
+    rot16<true>(x[1]);
+    bfly8<-1>(x[0]);
+    bfly8<-1>(x[1]);
+  }
+
+  // x[a][t] *= zeta_N^{k0 j} (CONJ: its conjugate), j=tid+NT*a+TPT*t
+  template<bool CONJ>
+  static __device__ __forceinline__ void residue(double2 (&x)[VT][8],
+                                                 const PlanDev& P,
+                                                 long long k0, int tid)
+  {
+    const double2 zst=zeta(P,modN(P,k0,TPT));
+#pragma unroll
+    for(int a=0; a < VT; ++a) {
+      double2 z=zeta(P,modN(P,k0,tid+NT*a));
+#pragma unroll
+      for(int t=0; t < 8; ++t) {
+        x[a][t]=cm<CONJ>(x[a][t],z);
+        if(t < 7) z=fmul(z,zst);
+      }
+    }
+  }
+};
+
+template<class LR, int MULT>
+__global__ void __launch_bounds__(512,1)
+fast_conv_rows_long(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
+                    double2 *f0, const double2 *f1, double scale,
+                    long long nrows, long long rs, int tabid)
+{
+  const int TPT=LR::TPT;
+  const int NT=LR::NT;
+  const int VT=LR::VT;
+  const int COLS=32*VT;   // TMEM columns of one parked set per warp
+  extern __shared__ __align__(16) double2 sm[];
+  __shared__ unsigned tmemBase;
+  double2 *w1s=sm;
+  double2 *buf=sm+LR::W1N;
+  const int tid=threadIdx.x;
+  const int L=P.jmax;
+
+  LR::init(P.tab[tabid].tw8,w1s,tid);
+  const int warp=tid >> 5;
+  if(warp == 0) tmemAlloc(&tmemBase,512);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // this warp's lane quadrant; 2*COLS columns per warp: [spectrum | sum]
+  const unsigned tY=tmemBase+(((unsigned) (32*(warp & 3))) << 16)+
+    (unsigned) ((warp >> 2)*2*COLS);
+  const unsigned tA=tY+COLS;
+
+  for(long long row=blockIdx.x; row < nrows; row += gridDim.x) {
+    double2 *g0=f0+row*rs;
+    const double2 *g1=f1+row*rs;
+    {
+      const long long nrow=row+gridDim.x;
+      if(nrow < nrows) { // pull the next row into L2 ahead of use
+        const char *p0=(const char *) (f0+nrow*rs);
+        const char *p1=(const char *) (f1+nrow*rs);
+        for(int off=tid*128; off < L*16; off += NT*128) {
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
+        }
+      }
+    }
+#pragma unroll 1
+    for(int isb=0; isb < nsb; ++isb) {
+      const long long k0=sbs[isb].k0;
+      // residue twiddles zeta_N^{k0 j}, j=tau_a+TPT*t: base times powers of
+      // the step zeta_N^{k0 TPT}
+      // (looked up at each use: registers are the scarce resource here)
+      double2 x[VT][8];
+      // ---- second input: transform, park the spectrum in tensor memory ----
+#pragma unroll
+      for(int a=0; a < VT; ++a)
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          const int j=tid+NT*a+TPT*t;
+          x[a][t]=j < L ? g1[j] : make_double2(0.0,0.0);
+        }
+      if(k0 != 0) LR::template residue<false>(x,P,k0,tid);
+      LR::forward(x,tid,w1s,buf);
+#pragma unroll
+      for(int a=0; a < VT; ++a) {
+        tmemSt4(tY+32*a,&x[a][0]);
+        tmemSt4(tY+32*a+16,&x[a][4]);
+      }
+      // ---- first input ----
+#pragma unroll
+      for(int a=0; a < VT; ++a)
+#pragma unroll
+        for(int t=0; t < 8; ++t) {
+          const int j=tid+NT*a+TPT*t;
+          x[a][t]=j < L ? g0[j] : make_double2(0.0,0.0);
+        }
+      if(k0 != 0) LR::template residue<false>(x,P,k0,tid);
+      LR::forward(x,tid,w1s,buf);
+      tmemWaitSt();
+      // ---- multiplier, inverse transform ----
+#pragma unroll
+      for(int a=0; a < VT; ++a)
+#pragma unroll
+        for(int h=0; h < 2; ++h) {
+          double2 y[4];
+          tmemLd4(tY+32*a+16*h,y);
+#pragma unroll
+          for(int t=0; t < 4; ++t)
+            x[a][4*h+t]=MULT == FFTWPP_MULT_BINARY ? fmul(x[a][4*h+t],y[t]) :
+              fmulc(x[a][4*h+t],y[t]);
+        }
+      LR::adjoint(x,tid,w1s,buf);
+      if(k0 != 0) LR::template residue<true>(x,P,k0,tid);
+      // ---- running sum over the residues (tensor memory) ----
+      if(isb > 0) {
+#pragma unroll
+        for(int a=0; a < VT; ++a)
+#pragma unroll
+          for(int h=0; h < 2; ++h) {
+            double2 y[4];
+            tmemLd4(tA+32*a+16*h,y);
+#pragma unroll
+            for(int t=0; t < 4; ++t) x[a][4*h+t]=x[a][4*h+t]+y[t];
+          }
+      }
+      if(isb+1 < nsb) {
+#pragma unroll
+        for(int a=0; a < VT; ++a) {
+          tmemSt4(tA+32*a,&x[a][0]);
+          tmemSt4(tA+32*a+16,&x[a][4]);
+        }
+        tmemWaitSt();
+      } else {
+#pragma unroll
+        for(int a=0; a < VT; ++a)
+#pragma unroll
+          for(int t=0; t < 8; ++t) {
+            const int j=tid+NT*a+TPT*t;
+            if(j < L)
+              g0[j]=make_double2(x[a][t].x*scale,x[a][t].y*scale);
+          }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if(warp == 0) tmemFree(tmemBase,512);
+}
+
 // FFTWPP_CONV_TMEM: 0 = off (register/shared-memory kernels of
 // fast_kernels.cu), 1 = radix-8 rows with TMEM parking (24 warps/SM),
 // 2 = one-warp rows with TMEM parking (16 rows in flight per SM)
@@ -346,6 +819,58 @@ int allowSmemT(K kernel, size_t bytes)
   return 0;
 }
 
+// Rows of m = 8192 points, p = 1 (L <= m), uniform sub-blocks.
+int tryLongRows(Plan *pl, void *const *f, uint32_t A, uint32_t B, int mult,
+                double scale, uint64_t nrows, uint64_t rs, cudaStream_t st)
+{
+  typedef LongRow16 LR;
+  const PlanDev& d=pl->dev;
+  if(pl->mmax != (unsigned) LR::M || d.kind != FFTWPP_KIND_COMPLEX ||
+     d.C != 1 || d.S != 1 || A != 2 || B != 1)
+    return 0;
+  if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
+  if(d.jmin != 0 || d.jmax > LR::M || pl->hsub.empty()) return 0;
+  for(size_t i=0; i < pl->hsub.size(); ++i)
+    if(pl->hsub[i].mlen != (unsigned) LR::M ||
+       pl->hsub[i].nout != (unsigned) LR::M || pl->hsub[i].flags != 0)
+      return 0;
+  int tabid=-1;
+  for(int k=0; k < 2; ++k)
+    if(d.tab[k].n == LR::M && d.tab[k].tw8) tabid=k;
+  if(tabid < 0) return 0;
+  if(nrows == 0) return 1;
+  int sms=148, dev=0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
+  const uint64_t grid=std::min<uint64_t>(nrows,(uint64_t) sms);
+  int rc=0;
+  static int engine=-1;
+  if(engine < 0) {
+    const char *e=getenv("FFTWPP_LONG_ENGINE");
+    engine=e && atoi(e) == 1 ? 1 : 2;
+  }
+#define LAUNCH_LONG(ENG, MU)                                                 \
+  {                                                                          \
+    const size_t smem=((size_t) ENG::W1N+ENG::BUF)*sizeof(double2);          \
+    rc=allowSmemT(fast_conv_rows_long<ENG,MU>,smem);                         \
+    if(rc) return rc;                                                        \
+    prof_begin(4*pl->tag+2,st);                                              \
+    fast_conv_rows_long<ENG,MU><<<(unsigned) grid,ENG::NT,smem,st>>>         \
+      (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],              \
+       (const double2 *) f[1],scale,(long long) nrows,(long long) rs,tabid); \
+  }
+  if(engine == 1) {
+    if(mult == FFTWPP_MULT_BINARY) LAUNCH_LONG(LongRow<13>,FFTWPP_MULT_BINARY)
+    else LAUNCH_LONG(LongRow<13>,FFTWPP_MULT_CORRELATION)
+  } else {
+    if(mult == FFTWPP_MULT_BINARY) LAUNCH_LONG(LongRow16,FFTWPP_MULT_BINARY)
+    else LAUNCH_LONG(LongRow16,FFTWPP_MULT_CORRELATION)
+  }
+#undef LAUNCH_LONG
+  rc=check_launch("fast_conv_rows_long",st);
+  return rc ? rc : 1;
+}
+
 } // namespace
 
 // Same contract as fast_try_convolve: 1 handled, 0 not applicable, <0 error.
@@ -353,6 +878,10 @@ int tmem_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
                       int mult, double scale, uint64_t nrows, uint64_t rs,
                       cudaStream_t st)
 {
+  {
+    int rc=tryLongRows(pl,f,A,B,mult,scale,nrows,rs,st);
+    if(rc != 0) return rc;
+  }
   FastInfo *fi=pl->fast;
   const int mode=tmemMode();
   if(mode == 0 || !fi || !fi->uniform || fi->nterm != 1) return 0;

@@ -68,8 +68,8 @@ def test_chooser_baseline_configs():
     assert [params(c, d) for d in range(3)] == [(128, 2, 3)] * 3
     c = fp.HybridConv([512] * 3, [1024] * 3, family=fp.FAMILY_REAL)       # cfg4 (headline)
     assert [params(c, d) for d in range(3)] == [(512, 1, 2)] * 3
-    c = fp.HybridConv([8192], [16384])                            # cfg5: two-stage inner
-    assert params(c, 0) == (256, 32, 64)
+    c = fp.HybridConv([8192], [16384])                # cfg5: fused long rows (tensor memory)
+    assert params(c, 0) == (8192, 1, 2)
 
 
 def test_device_multiplier_needs_host_function():
