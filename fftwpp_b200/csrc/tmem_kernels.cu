@@ -265,205 +265,82 @@ fast_conv_rows_wtm(PlanDev P, const SubBlockDev *__restrict__ sbs,
 }
 
 // ---------------------------------------------------------------------------
-// Long rows: m = 8192 (one CTA per row, fully fused)
+// Long rows: m = 8192 and m = 4096, one CTA per row, fully fused
 // ---------------------------------------------------------------------------
 // A row of 8192 complex words is 128 KB: the padded exchange buffer of ONE
 // transform fills most of an SM's shared memory, so the register/shared-memory
 // kernels stop at m = 4096 and longer rows used to take the two-stage path
-// (three HBM round trips).  Here 512 threads each play two of the 1024
-// "virtual threads" of RegFFT<13> (16 complex points per thread, 64
+// (three HBM round trips).  Here every thread owns 16 complex points (64
 // registers), and everything that must survive a transform lives in tensor
 // memory: the transformed second input (64 columns per warp) and the running
-// sum over residues (64 more) -- 4 warps per lane quadrant x 128 columns = all
-// 512 columns, 256 KB, of the SM's TMEM.  HBM traffic is the algorithmic
-// minimum (read both inputs, write one output; the second residue re-reads
-// its inputs from L2).
+// sum over residues (64 more) -- for m = 8192, 4 warps per lane quadrant x 128
+// columns = all 512 columns, 256 KB, of the SM's TMEM; for m = 4096 two CTAs
+// of 256 columns each.  HBM traffic is the algorithmic minimum (read both
+// inputs, write one output; the second residue re-reads its inputs from L2 --
+// an L2 prefetch of the next row evicts them and measured 7 % slower).
 //
 // Reference loop being replaced: Convolution::convolveRaw over the residues
 // with multBinary/multcorrelation (convolve.cc:7513-7575,33-110) on
 // fftPad::forward1/backward1 (convolve.cc:849-958,1482-1546), p=1, L <= m.
-template<int LG>
-struct LongRow {
-  typedef RegFFT<LG> RF;
-  static const int M=RF::N;
-  static const int TPT=RF::TPT;     // virtual threads
-  static const int NT=512;          // physical threads
-  static const int VT=TPT/NT;       // virtual threads per physical thread
-  static const int NR8=RF::NR8;
-  static const int BUF=M+M/8;
 
-  // compact table of the radix-8 twiddle bases: pass i holds 2^ls_i entries
-  static __host__ __device__ constexpr int w1Off(int i) {
-    int off=0;
-    for(int k=0; k < i; ++k) off += 1 << (LG-3*(k+1));
-    return off;
-  }
-  static constexpr int W1N=(w1Off(NR8)+15) & ~15;
-
-  static __device__ __forceinline__ int pad(int p) {return p+(p >> 3);}
-
-  // radix-8 twiddle bases: the u=1 block of every pass of the tw8 table
-  static __device__ __forceinline__ void init(const double2 *tw, double2 *w1s,
-                                              int tid)
-  {
-#pragma unroll
-    for(int i=0; i < NR8; ++i) {
-      const int ls=LG-3*(i+1);
-      if(ls > 0)
-        for(int j=tid; j < (1 << ls); j += NT)
-          w1s[w1Off(i)+j]=__ldg(tw+RF::twOff(i)+j);
-    }
-  }
-
-  // x[u] *= w^u (CONJ: conj(w)^u), the powers formed by products as they
-  // are needed so that few of them are live at a time
-  template<bool CONJ>
-  static __device__ __forceinline__ void twiddle(double2 (&x)[8], double2 w1)
-  {
-    if(CONJ) w1.y=-w1.y;
-    x[1]=fmul(x[1],w1);
-    const double2 w2=fmul(w1,w1);
-    x[2]=fmul(x[2],w2);
-    const double2 w3=fmul(w1,w2);
-    x[3]=fmul(x[3],w3);
-    const double2 w4=fmul(w2,w2);
-    x[4]=fmul(x[4],w4);
-    x[5]=fmul(x[5],fmul(w1,w4));
-    x[6]=fmul(x[6],fmul(w3,w3));
-    x[7]=fmul(x[7],fmul(w3,w4));
-  }
-
-  static __device__ __forceinline__ void exchange(double2 (&x)[VT][8], int tid,
-                                                  int lsFrom, int lsTo,
-                                                  double2 *buf)
-  {
-    __syncthreads();
-#pragma unroll
-    for(int a=0; a < VT; ++a)
-#pragma unroll
-      for(int t=0; t < 8; ++t)
-        buf[pad(RF::pos(tid+NT*a,t,lsFrom))]=x[a][t];
-    __syncthreads();
-#pragma unroll
-    for(int a=0; a < VT; ++a)
-#pragma unroll
-      for(int t=0; t < 8; ++t)
-        x[a][t]=buf[pad(RF::pos(tid+NT*a,t,lsTo))];
-  }
-
-  // x[a][t] *= zeta_N^{k0 j} (CONJ: its conjugate), j=tau_a+TPT*t
-  template<bool CONJ>
-  static __device__ __forceinline__ void residue(double2 (&x)[VT][8],
-                                                 const PlanDev& P,
-                                                 long long k0, int tid)
-  {
-    const double2 zst=zeta(P,modN(P,k0,TPT));
-#pragma unroll
-    for(int a=0; a < VT; ++a) {
-      double2 z=zeta(P,modN(P,k0,tid+NT*a));
-#pragma unroll
-      for(int t=0; t < 8; ++t) {
-        x[a][t]=CONJ ? fmulc(x[a][t],z) : fmul(x[a][t],z);
-        if(t < 7) z=fmul(z,zst);
-      }
-    }
-  }
-
-  // in: x[a][t]=W[tau_a+TPT*t], tau_a=tid+NT*a; out: scrambled position
-  // 8*tau_a+e (RegFFT<LG>::forward with per-array virtual threads)
-  static __device__ __forceinline__ void forward(double2 (&x)[VT][8], int tid,
-                                                 const double2 *w1s,
-                                                 double2 *buf)
-  {
-#pragma unroll
-    for(int i=0; i < NR8; ++i) {
-      const int ls=LG-3*(i+1);
-#pragma unroll
-      for(int a=0; a < VT; ++a) {
-        bfly8<1>(x[a]);
-        if(ls > 0)
-          twiddle<false>(x[a],w1s[w1Off(i)+((tid+NT*a) & ((1 << ls)-1))]);
-      }
-      const int lsNext=(i+1 < NR8) ? LG-3*(i+2) : 0;
-      if(i+1 < NR8 || RF::REM > 0) exchange(x,tid,ls,lsNext,buf);
-    }
-#pragma unroll
-    for(int a=0; a < VT; ++a) {
-      if(RF::REM == 2) {
-        bfly4<1>(x[a][0],x[a][1],x[a][2],x[a][3]);
-        bfly4<1>(x[a][4],x[a][5],x[a][6],x[a][7]);
-      } else if(RF::REM == 1) {
-        bfly2(x[a][0],x[a][1]);
-        bfly2(x[a][2],x[a][3]);
-        bfly2(x[a][4],x[a][5]);
-        bfly2(x[a][6],x[a][7]);
-      }
-    }
-  }
-
-  // exact adjoint of forward()
-  static __device__ __forceinline__ void adjoint(double2 (&x)[VT][8], int tid,
-                                                 const double2 *w1s,
-                                                 double2 *buf)
-  {
-#pragma unroll
-    for(int a=0; a < VT; ++a) {
-      if(RF::REM == 2) {
-        bfly4<-1>(x[a][0],x[a][1],x[a][2],x[a][3]);
-        bfly4<-1>(x[a][4],x[a][5],x[a][6],x[a][7]);
-      } else if(RF::REM == 1) {
-        bfly2(x[a][0],x[a][1]);
-        bfly2(x[a][2],x[a][3]);
-        bfly2(x[a][4],x[a][5]);
-        bfly2(x[a][6],x[a][7]);
-      }
-    }
-#pragma unroll
-    for(int i=NR8-1; i >= 0; --i) {
-      const int ls=LG-3*(i+1);
-      const int lsPrev=(i+1 < NR8) ? LG-3*(i+2) : 0;
-      if(i+1 < NR8 || RF::REM > 0) exchange(x,tid,lsPrev,ls,buf);
-#pragma unroll
-      for(int a=0; a < VT; ++a) {
-        if(ls > 0)
-          twiddle<true>(x[a],w1s[w1Off(i)+((tid+NT*a) & ((1 << ls)-1))]);
-        bfly8<-1>(x[a]);
-      }
-    }
-  }
-};
-
-// 8192 = 16 x 512.  A thread's 16 points are 512 apart, so the first pass is a
-// radix-16 butterfly in registers; ONE CTA-wide exchange then hands each of
-// the 16 warps one 512-point transform (two virtual threads per lane), whose
-// two remaining exchanges need only __syncwarp().  Three exchanges per
-// transform instead of four, and two CTA barriers instead of eight, so the
-// warps drift apart and overlap butterflies with shared-memory traffic.
-// The order of the transformed points differs from RegFFT<13>'s; the fused
-// convolution only multiplies pointwise, so any order shared by forward()
-// and adjoint() serves.
+// m = 16 x SUB (8192 = 16 x 512, 4096 = 16 x 256), SUB threads.  A thread's 16
+// points are SUB apart, so the first pass is a radix-16 butterfly in
+// registers; ONE CTA-wide exchange then hands every warp whole sub-transforms
+// (8192: one of 512 points, two virtual threads per lane; 4096: two of 256
+// points, one virtual thread per lane each), whose remaining exchanges need
+// only __syncwarp().  Compared with RegFFT<LG> over the whole row: one
+// exchange less for 8192, and two CTA barriers per transform instead of six or
+// eight, so the warps drift apart and overlap butterflies with shared-memory
+// traffic.  The order of the transformed points differs from RegFFT<LG>'s; the
+// fused convolution only multiplies pointwise, so any order shared by
+// forward() and adjoint() serves.
+template<int LGV>
 struct LongRow16 {
-  typedef RegFFT<9> R9;
-  static const int LG=13;
+  static const int LG=LGV;
+  static const int SUBLG=LG-4;
+  typedef RegFFT<SUBLG> RS;
   static const int M=1 << LG;
-  static const int NT=512;
+  static const int SUB=1 << SUBLG;       // points of a sub-transform
+  static const int NT=SUB;               // threads
   static const int VT=2;
   static const int TPT=NT*VT;
-  static const int SUB=512;              // points of a warp's transform
+  static const int NW=NT/32;             // warps
+  static const int TS=SUB/8;             // virtual threads of a sub-transform
   static const int SUBBUF=SUB+SUB/8;
   static const int BUF=16*SUBBUF;
-  // tables: w_M^j, j < 512 | w_512^j, j < 64 | w_64^j, j < 8
-  static const int W1N=512+64+16;
+  static const int NR8=RS::NR8;
+  static_assert(TS == 64 || TS == 32,"one or two sub-transforms per warp");
+
+  // tables: w_M^j, j < SUB | per radix-8 pass i of the sub-transform (legs
+  // 2^ls_i apart, ls_i > 0): w_SUB^{j 8^i}, j < 2^ls_i
+  static __host__ __device__ constexpr int wOff(int i) {
+    int off=SUB;
+    for(int k=0; k < i; ++k) off += 1 << (SUBLG-3*(k+1));
+    return off;
+  }
+  static constexpr int W1N=(wOff(NR8)+15) & ~15;
 
   static __device__ __forceinline__ int pad(int p) {return p+(p >> 3);}
+  // sub-transform and virtual thread served by array a of this thread
+  static __device__ __forceinline__ int ksub(int warp, int a) {
+    return TS == 64 ? warp : warp+NW*a;
+  }
+  static __device__ __forceinline__ int tau(int lane, int a) {
+    return TS == 64 ? lane+32*a : lane;
+  }
 
   static __device__ __forceinline__ void init(const double2 *tw, double2 *w1s,
                                               int tid)
   {
     // the u=1 block of pass 0 of the tw8 table holds w_M^j, j < M/8
-    for(int j=tid; j < 512; j += NT) w1s[j]=__ldg(tw+j);
-    for(int j=tid; j < 64; j += NT) w1s[512+j]=__ldg(tw+16*j);
-    for(int j=tid; j < 8; j += NT) w1s[576+j]=__ldg(tw+128*j);
+    for(int j=tid; j < SUB; j += NT) w1s[j]=__ldg(tw+j);
+#pragma unroll
+    for(int i=0; i < NR8; ++i) {
+      const int ls=SUBLG-3*(i+1);
+      if(ls > 0)
+        for(int j=tid; j < (1 << ls); j += NT)
+          w1s[wOff(i)+j]=__ldg(tw+((16*j) << (3*i)));
+    }
   }
 
   template<bool CONJ>
@@ -517,7 +394,7 @@ struct LongRow16 {
     x[1][7]=cm<CONJ>(x[1][7],fmul(w7,w8));
   }
 
-  // x[1][k] *= exp(2 pi i k/16) (CONJ: its conjugate)
+  // z[k] *= exp(2 pi i k/16) (CONJ: its conjugate)
   template<bool CONJ>
   static __device__ __forceinline__ void rot16(double2 (&z)[8])
   {
@@ -533,32 +410,49 @@ struct LongRow16 {
     z[7]=cm<CONJ>(z[7],make_double2(-c,s));
   }
 
-  // exchange inside a warp's 512-point region
+  // exchange inside the warp's sub-transform regions
   static __device__ __forceinline__ void warpExchange(double2 (&x)[VT][8],
-                                                      int lane, int lsFrom,
-                                                      int lsTo, double2 *reg)
+                                                      int warp, int lane,
+                                                      int lsFrom, int lsTo,
+                                                      double2 *buf)
   {
     __syncwarp();
 #pragma unroll
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        reg[pad(R9::pos(lane+32*a,t,lsFrom))]=x[a][t];
+        buf[ksub(warp,a)*SUBBUF+pad(RS::pos(tau(lane,a),t,lsFrom))]=x[a][t];
     __syncwarp();
 #pragma unroll
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        x[a][t]=reg[pad(R9::pos(lane+32*a,t,lsTo))];
+        x[a][t]=buf[ksub(warp,a)*SUBBUF+pad(RS::pos(tau(lane,a),t,lsTo))];
   }
 
-  // in: x[a][t]=W[tid+512*(a+2t)]; out: some fixed order of the transform
+  template<int SIGN>
+  static __device__ __forceinline__ void remainder(double2 (&x)[VT][8])
+  {
+#pragma unroll
+    for(int a=0; a < VT; ++a) {
+      if(RS::REM == 2) {
+        bfly4<SIGN>(x[a][0],x[a][1],x[a][2],x[a][3]);
+        bfly4<SIGN>(x[a][4],x[a][5],x[a][6],x[a][7]);
+      } else if(RS::REM == 1) {
+        bfly2(x[a][0],x[a][1]);
+        bfly2(x[a][2],x[a][3]);
+        bfly2(x[a][4],x[a][5]);
+        bfly2(x[a][6],x[a][7]);
+      }
+    }
+  }
+
+  // in: x[a][t]=W[tid+NT*(a+2t)]; out: some fixed order of the transform
   static __device__ __forceinline__ void forward(double2 (&x)[VT][8], int tid,
                                                  const double2 *w1s,
                                                  double2 *buf)
   {
     const int warp=tid >> 5, lane=tid & 31;
-    double2 *reg=buf+warp*SUBBUF;
     // radix 16 over s=a+2t: y_k = sum_s x_s w_16^{sk}, k=k8+8a
     bfly8<1>(x[0]);
     bfly8<1>(x[1]);
@@ -566,7 +460,7 @@ struct LongRow16 {
 #pragma unroll
     for(int k=0; k < 8; ++k) bfly2(x[0][k],x[1][k]);
     twiddle16<false>(x,w1s[tid]);
-    // y_k[tid] -> transform k, column tid
+    // y_k[tid] -> sub-transform k, column tid
     __syncthreads();
 #pragma unroll
     for(int a=0; a < VT; ++a)
@@ -578,20 +472,21 @@ struct LongRow16 {
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        x[a][t]=reg[pad(lane+32*a+64*t)];
-    // 512 points per warp: RegFFT<9> with two virtual threads per lane
+        x[a][t]=buf[ksub(warp,a)*SUBBUF+pad(tau(lane,a)+TS*t)];
+    // the sub-transforms: RegFFT<SUBLG> inside the warp
 #pragma unroll
-    for(int i=0; i < 3; ++i) {
-      const int ls=9-3*(i+1);
+    for(int i=0; i < NR8; ++i) {
+      const int ls=SUBLG-3*(i+1);
 #pragma unroll
       for(int a=0; a < VT; ++a) {
         bfly8<1>(x[a]);
         if(ls > 0)
-          twiddle<false>(x[a],w1s[(i == 0 ? 512 : 576)+
-                                  ((lane+32*a) & ((1 << ls)-1))]);
+          twiddle<false>(x[a],w1s[wOff(i)+(tau(lane,a) & ((1 << ls)-1))]);
       }
-      if(i < 2) warpExchange(x,lane,ls,ls-3,reg);
+      const int lsNext=(i+1 < NR8) ? SUBLG-3*(i+2) : 0;
+      if(i+1 < NR8 || RS::REM > 0) warpExchange(x,warp,lane,ls,lsNext,buf);
     }
+    remainder<1>(x);
   }
 
   // exact adjoint of forward()
@@ -600,16 +495,16 @@ struct LongRow16 {
                                                  double2 *buf)
   {
     const int warp=tid >> 5, lane=tid & 31;
-    double2 *reg=buf+warp*SUBBUF;
+    remainder<-1>(x);
 #pragma unroll
-    for(int i=2; i >= 0; --i) {
-      const int ls=9-3*(i+1);
-      if(i < 2) warpExchange(x,lane,ls-3,ls,reg);
+    for(int i=NR8-1; i >= 0; --i) {
+      const int ls=SUBLG-3*(i+1);
+      const int lsPrev=(i+1 < NR8) ? SUBLG-3*(i+2) : 0;
+      if(i+1 < NR8 || RS::REM > 0) warpExchange(x,warp,lane,lsPrev,ls,buf);
 #pragma unroll
       for(int a=0; a < VT; ++a) {
         if(ls > 0)
-          twiddle<true>(x[a],w1s[(i == 0 ? 512 : 576)+
-                                 ((lane+32*a) & ((1 << ls)-1))]);
+          twiddle<true>(x[a],w1s[wOff(i)+(tau(lane,a) & ((1 << ls)-1))]);
         bfly8<-1>(x[a]);
       }
     }
@@ -618,7 +513,7 @@ struct LongRow16 {
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        reg[pad(lane+32*a+64*t)]=x[a][t];
+        buf[ksub(warp,a)*SUBBUF+pad(tau(lane,a)+TS*t)]=x[a][t];
     __syncthreads();
 #pragma unroll
     for(int a=0; a < VT; ++a)
@@ -653,7 +548,7 @@ struct LongRow16 {
 };
 
 template<class LR, int MULT>
-__global__ void __launch_bounds__(512,1)
+__global__ void __launch_bounds__(LR::NT,512/LR::NT)
 fast_conv_rows_long(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
                     double2 *f0, const double2 *f1, double scale,
                     long long nrows, long long rs, int tabid)
@@ -662,6 +557,7 @@ fast_conv_rows_long(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   const int NT=LR::NT;
   const int VT=LR::VT;
   const int COLS=32*VT;   // TMEM columns of one parked set per warp
+  const int TCOLS=(NT/128)*2*COLS; // of the CTA: NT/128 warps per lane quadrant
   extern __shared__ __align__(16) double2 sm[];
   __shared__ unsigned tmemBase;
   double2 *w1s=sm;
@@ -671,7 +567,7 @@ fast_conv_rows_long(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
 
   LR::init(P.tab[tabid].tw8,w1s,tid);
   const int warp=tid >> 5;
-  if(warp == 0) tmemAlloc(&tmemBase,512);
+  if(warp == 0) tmemAlloc(&tmemBase,TCOLS);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -683,17 +579,6 @@ fast_conv_rows_long(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   for(long long row=blockIdx.x; row < nrows; row += gridDim.x) {
     double2 *g0=f0+row*rs;
     const double2 *g1=f1+row*rs;
-    {
-      const long long nrow=row+gridDim.x;
-      if(nrow < nrows) { // pull the next row into L2 ahead of use
-        const char *p0=(const char *) (f0+nrow*rs);
-        const char *p1=(const char *) (f1+nrow*rs);
-        for(int off=tid*128; off < L*16; off += NT*128) {
-          asm volatile("prefetch.global.L2 [%0];" :: "l"(p0+off));
-          asm volatile("prefetch.global.L2 [%0];" :: "l"(p1+off));
-        }
-      }
-    }
 #pragma unroll 1
     for(int isb=0; isb < nsb; ++isb) {
       const long long k0=sbs[isb].k0;
@@ -774,7 +659,7 @@ fast_conv_rows_long(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if(warp == 0) tmemFree(tmemBase,512);
+  if(warp == 0) tmemFree(tmemBase,TCOLS);
 }
 
 // FFTWPP_CONV_TMEM: 0 = off (register/shared-memory kernels of
@@ -819,21 +704,12 @@ int allowSmemT(K kernel, size_t bytes)
   return 0;
 }
 
-// Rows of m = 8192 points, p = 1 (L <= m), uniform sub-blocks.
-int tryLongRows(Plan *pl, void *const *f, uint32_t A, uint32_t B, int mult,
-                double scale, uint64_t nrows, uint64_t rs, cudaStream_t st)
+// Rows of m = 8192 or 4096 points, p = 1 (L <= m), uniform sub-blocks.
+template<class LR>
+int launchLongRows(Plan *pl, void *const *f, int mult, double scale,
+                   uint64_t nrows, uint64_t rs, cudaStream_t st)
 {
-  typedef LongRow16 LR;
   const PlanDev& d=pl->dev;
-  if(pl->mmax != (unsigned) LR::M || d.kind != FFTWPP_KIND_COMPLEX ||
-     d.C != 1 || d.S != 1 || A != 2 || B != 1)
-    return 0;
-  if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
-  if(d.jmin != 0 || d.jmax > LR::M || pl->hsub.empty()) return 0;
-  for(size_t i=0; i < pl->hsub.size(); ++i)
-    if(pl->hsub[i].mlen != (unsigned) LR::M ||
-       pl->hsub[i].nout != (unsigned) LR::M || pl->hsub[i].flags != 0)
-      return 0;
   int tabid=-1;
   for(int k=0; k < 2; ++k)
     if(d.tab[k].n == LR::M && d.tab[k].tw8) tabid=k;
@@ -842,33 +718,46 @@ int tryLongRows(Plan *pl, void *const *f, uint32_t A, uint32_t B, int mult,
   int sms=148, dev=0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
-  const uint64_t grid=std::min<uint64_t>(nrows,(uint64_t) sms);
+  const uint64_t grid=std::min<uint64_t>(nrows,(uint64_t) sms*(512/LR::NT));
+  const size_t smem=((size_t) LR::W1N+LR::BUF)*sizeof(double2);
   int rc=0;
-  static int engine=-1;
-  if(engine < 0) {
-    const char *e=getenv("FFTWPP_LONG_ENGINE");
-    engine=e && atoi(e) == 1 ? 1 : 2;
-  }
-#define LAUNCH_LONG(ENG, MU)                                                 \
-  {                                                                          \
-    const size_t smem=((size_t) ENG::W1N+ENG::BUF)*sizeof(double2);          \
-    rc=allowSmemT(fast_conv_rows_long<ENG,MU>,smem);                         \
-    if(rc) return rc;                                                        \
-    prof_begin(4*pl->tag+2,st);                                              \
-    fast_conv_rows_long<ENG,MU><<<(unsigned) grid,ENG::NT,smem,st>>>         \
-      (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],              \
-       (const double2 *) f[1],scale,(long long) nrows,(long long) rs,tabid); \
-  }
-  if(engine == 1) {
-    if(mult == FFTWPP_MULT_BINARY) LAUNCH_LONG(LongRow<13>,FFTWPP_MULT_BINARY)
-    else LAUNCH_LONG(LongRow<13>,FFTWPP_MULT_CORRELATION)
+  if(mult == FFTWPP_MULT_BINARY) {
+    rc=allowSmemT(fast_conv_rows_long<LR,FFTWPP_MULT_BINARY>,smem);
+    if(rc) return rc;
+    prof_begin(4*pl->tag+2,st);
+    fast_conv_rows_long<LR,FFTWPP_MULT_BINARY><<<(unsigned) grid,LR::NT,smem,st>>>
+      (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],
+       (const double2 *) f[1],scale,(long long) nrows,(long long) rs,tabid);
   } else {
-    if(mult == FFTWPP_MULT_BINARY) LAUNCH_LONG(LongRow16,FFTWPP_MULT_BINARY)
-    else LAUNCH_LONG(LongRow16,FFTWPP_MULT_CORRELATION)
+    rc=allowSmemT(fast_conv_rows_long<LR,FFTWPP_MULT_CORRELATION>,smem);
+    if(rc) return rc;
+    prof_begin(4*pl->tag+2,st);
+    fast_conv_rows_long<LR,FFTWPP_MULT_CORRELATION>
+      <<<(unsigned) grid,LR::NT,smem,st>>>
+      (pl->dev,pl->dsub,(int) pl->hsub.size(),(double2 *) f[0],
+       (const double2 *) f[1],scale,(long long) nrows,(long long) rs,tabid);
   }
-#undef LAUNCH_LONG
   rc=check_launch("fast_conv_rows_long",st);
   return rc ? rc : 1;
+}
+
+int tryLongRows(Plan *pl, void *const *f, uint32_t A, uint32_t B, int mult,
+                double scale, uint64_t nrows, uint64_t rs, cudaStream_t st)
+{
+  const PlanDev& d=pl->dev;
+  const unsigned M=pl->mmax;
+  if((M != 8192 && M != 4096) || d.kind != FFTWPP_KIND_COMPLEX || d.C != 1 ||
+     d.S != 1 || A != 2 || B != 1)
+    return 0;
+  if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
+  if(d.jmin != 0 || d.jmax > (int) M || pl->hsub.empty()) return 0;
+  for(size_t i=0; i < pl->hsub.size(); ++i)
+    if(pl->hsub[i].mlen != M || pl->hsub[i].nout != M ||
+       pl->hsub[i].flags != 0)
+      return 0;
+  if(M == 8192)
+    return launchLongRows<LongRow16<13> >(pl,f,mult,scale,nrows,rs,st);
+  return launchLongRows<LongRow16<12> >(pl,f,mult,scale,nrows,rs,st);
 }
 
 } // namespace

@@ -1,4 +1,4 @@
-"""Rows of m = 8192 points on the tensor-memory kernel (fast_conv_rows_long,
+"""Rows of m = 8192 and m = 4096 points on the tensor-memory kernel (fast_conv_rows_long,
 csrc/tmem_kernels.cu): the fully fused residue loop of Convolution::convolveRaw
 (reference convolve.cc:7513-7575) for 4096 < L <= 8192, against the numpy oracle.
 Covers full rows, zero-padded rows (L < m), odd L, the correlation multiplier,
@@ -24,19 +24,21 @@ def rows_want(f, g, M, corr=False):
     return h[:, :f.shape[1]]
 
 
-@pytest.mark.parametrize("L,M,force", [(8192, 16384, False), (8192, 12289, True),
-                                       (5000, 10000, True), (4097, 8194, True),
-                                       (8191, 16382, True), (6144, 16384, True)])
+@pytest.mark.parametrize("L,M,m,force", [(8192, 16384, 8192, False), (8192, 12289, 8192, True),
+                                         (5000, 10000, 8192, True), (4097, 8194, 8192, True),
+                                         (8191, 16382, 8192, True), (6144, 16384, 8192, True),
+                                         (4096, 8192, 4096, False), (3000, 6000, 4096, True),
+                                         (2049, 4098, 4096, True), (4095, 8190, 4096, True)])
 @pytest.mark.parametrize("mult", [fp.MULT_BINARY, fp.MULT_CORRELATION])
-def test_long_rows(L, M, force, mult):
+def test_long_rows(L, M, m, force, mult):
     import torch
     rng = np.random.default_rng(L + mult)
     rows = 5
-    conv = fp.HybridConv([L], [M], m=[8192] if force else None, mult=mult)
+    conv = fp.HybridConv([L], [M], m=[m] if force else None, mult=mult)
     p = conv.params(0)
-    assert (p["m"], p["p"], p["q"]) == (8192, 1, 2)
+    assert (p["m"], p["p"], p["q"]) == (m, 1, 2)
     f, g = crand(rng, rows, L), crand(rng, rows, L)
-    want = rows_want(f, g, 16384, corr=mult == fp.MULT_CORRELATION)
+    want = rows_want(f, g, 2 * m, corr=mult == fp.MULT_CORRELATION)
     d = [torch.from_numpy(f.copy()).cuda(), torch.from_numpy(g.copy()).cuda()]
     before = fp.lib.fftwpp_gpu_launch_count()
     conv.convolve_rows(d, rows, L)
@@ -44,7 +46,7 @@ def test_long_rows(L, M, force, mult):
     assert fp.lib.fftwpp_gpu_launch_count() - before == 1     # one fused launch
     got = d[0].cpu().numpy()
     per_row = np.sqrt(np.sum(np.abs(got - want) ** 2, axis=1) / np.sum(np.abs(want) ** 2, axis=1))
-    assert per_row.max() < O.tolerance(16384)
+    assert per_row.max() < O.tolerance(2 * m)
     assert np.array_equal(d[1].cpu().numpy(), g)              # second input untouched
     conv.close()
 
