@@ -72,6 +72,27 @@ def test_chooser_baseline_configs():
     assert params(c, 0) == (8192, 1, 2)
 
 
+def test_partially_forced_parameters():
+    """m alone (D = 0, I = -1), as Application(A,B,mult,threads,verbose,m) in the
+    reference (convolve.h:95-123): m is honoured, D is chosen.  (Used to divide
+    by zero in the forced constructor.)"""
+    for kind_args in (dict(), dict(family=fp.FAMILY_HERMITIAN), dict(family=fp.FAMILY_REAL)):
+        c = fp.HybridConv([512], [1000], m=[256], **kind_args)
+        p = c.params(0)
+        assert p["m"] == 256 and p["D"] >= 1 and p["m"] * p["q"] >= 1000
+        c.close()
+    c = fp.HybridConv([5000], [10000], m=[8192])
+    assert (c.params(0)["m"], c.params(0)["p"], c.params(0)["q"]) == (8192, 1, 2)
+    c.close()
+    os.environ["FFTWPP_NO_LONG_ROWS"] = "1"       # the two-stage path for long rows
+    try:
+        c = fp.HybridConv([8192], [16384])
+        assert c.params(0)["p"] > 2
+        c.close()
+    finally:
+        del os.environ["FFTWPP_NO_LONG_ROWS"]
+
+
 def test_device_multiplier_needs_host_function():
     """fftwpp_conv_create_custom identifies the device multiplier by the host
     function's address, so a NULL host function is refused."""
