@@ -3,22 +3,26 @@
 //
 // The fused row kernels of fast_kernels.cu keep the transformed second input
 // in registers while the first input is transformed, and park the running sum
-// over residues in shared memory: 128 registers, 16 warps per SM, and the
-// shared-memory pipe -- the busiest unit of the kernel -- also carries the
-// parking traffic.  Here both live in TMEM (256 KB per SM, otherwise unused on
-// this path: no tensor-core math): each thread stores its 8 complex values to
-// its own TMEM lane with tcgen05.st and takes them back with tcgen05.ld when
-// the multiplier / the accumulation needs them.  One transform's worth of
-// registers is live at a time: 80 registers, 3 CTAs = 24 warps per SM, and no
-// parking traffic on the LSU pipe.
+// over residues in shared memory.  Here both live in TMEM (256 KB per SM,
+// otherwise unused on this path: no tensor-core math): each thread stores its
+// complex values to its own TMEM lane with tcgen05.st and takes them back with
+// tcgen05.ld when the multiplier / the accumulation needs them.
+//
+//   fast_conv_rows_long  rows of m = 8192 and m = 4096 points (default for
+//                        those shapes): 16 points per thread; without TMEM
+//                        the spectrum and the sum would not fit on chip
+//   fast_conv_rows_tm    m = 512, radix-8 rows, 80 registers, 24 warps/SM
+//   fast_conv_rows_wtm   m = 512, one-warp rows (warpfft.cuh)
+//                        (both opt-in, FFTWPP_CONV_TMEM=1/2: measured slower
+//                        than fast_conv_rows_q2, kept as documented experiments)
 //
 // Reference loop being replaced: Convolution::convolveRaw residue loop with
 // multBinary/multcorrelation (convolve.cc:7513-7575,33-110), fftPad forward1/
-// backward1 (convolve.cc:849-958,1482-1546); shape p=1, q=2, L == m == 512.
+// backward1 (convolve.cc:849-958,1482-1546); shape p=1, L <= m.
 //
-// TMEM rules used: allocation by one warp (power-of-two columns, here 128 per
-// CTA), a warp reaches only the lanes of its quadrant 32*(warp%4), shape
-// 32x32b = one 32-bit word per thread per column.
+// TMEM rules used: allocation by one warp (power-of-two columns), a warp
+// reaches only the lanes of its quadrant 32*(warp%4), shape 32x32b = one
+// 32-bit word per thread per column (tmem.cuh).
 
 #include "regfft.cuh"
 #include "warpfft.cuh"
