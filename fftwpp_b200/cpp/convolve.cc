@@ -358,6 +358,15 @@ static bool longRows()
   return !(s && *s && *s != '0');
 }
 
+// Rows of 8192 points exist only as the fused A=2, B=1 tensor-memory kernel
+// (fast_conv_rows_long): stage B of a two-stage transform may use them for the
+// built-in binary multipliers only.
+static bool longStageB(const Application& app)
+{
+  return app.A == 2 && app.B == 1 &&
+    (app.mult == multBinary || app.mult == multcorrelation);
+}
+
 void fftBase::choose(bool Explicit)
 {
   const bool mForced=app.m >= 1;
@@ -380,7 +389,7 @@ void fftBase::choose(bool Explicit)
     cand.push_back(nextfftsize(ceilquotient(M,2)));
     cand.push_back(nextfftsize(M));
     if(C == 1) cand.push_back(ceilpow2(M));
-    for(size_t mi=16; mi < H && mi <= 4096; mi *= 2)
+    for(size_t mi=16; mi < H && mi <= 8192; mi *= 2)
       cand.push_back(mi);
   }
 
@@ -405,7 +414,8 @@ void fftBase::choose(bool Explicit)
     size_t lane=(C == 1 ? (app.A+app.B)*Lin*word+
                  std::max(app.A,app.B)*mc*sizeof(Complex) :
                  Lin*word+mc*sizeof(Complex));
-    bool inner=qc > 1 && innerEligible(kind(),L,mc,pc,C,S);
+    bool inner=qc > 1 && innerEligible(kind(),L,mc,pc,C,S) &&
+      (mc <= 4096 || longStageB(app));
     // the fused register kernels (fast_kernels.cu) hold a whole power-of-two
     // row of up to 4096 points (2048 with two input terms) on chip
     // regardless of the generic kernels' tile estimate; p=1, q=2 rows of 8192
@@ -422,8 +432,12 @@ void fftBase::choose(bool Explicit)
       double lm=log2((double) mc), lp=log2((double) pc);
       // measured on B200 (L=2^13 rows and L=2^20): flat optimum around
       // m = 4p..8p (the fused stage prefers long rows, the strided stage
-      // short transforms)
+      // short transforms); rows of m >= 4096 with the tensor-memory row
+      // kernel serving stage B (A=2, B=1, binary multipliers) are cheaper
+      // (profiles/long_rows_r02.jsonl: L=2^20 m=4096 0.128 ms, m=2048 0.150;
+      // L=2^22 m=8192 0.523, m=4096 0.575, m=2048 0.679)
       cost=N*(lm+lp+8.0+0.25*fabs(lm-lp-2.5));
+      if(mc >= 4096 && longStageB(app)) cost *= mc == 8192 ? 0.87 : 0.88;
     } else {
       cost=N*(log2((double) mc)+2.0+pc)*(ispow2(mc) ? 1.0 : 2.5);
       if(pc > 2) cost *= 1.0+0.25*pc;
@@ -489,7 +503,7 @@ bool fftBase::innerEligible(Kind kind, size_t L, size_t m, size_t p, size_t C,
                             size_t S)
 {
   return kind == COMPLEX && C == 1 && S == 1 && p > 2 && ispow2(m) &&
-    ispow2(p) && m >= 16 && m <= 4096 && p >= 16 && p <= 4096 && L == p*m;
+    ispow2(p) && m >= 16 && m <= 8192 && p >= 16 && p <= 4096 && L == p*m;
 }
 
 // Stage A: the reference's "L'=p, M'=q, m'=p, p'=1, q'=n" transform
@@ -753,7 +767,8 @@ void fftPad::init()
     }
   }
   buildPlan(sub);
-  twoStage=q > 1 && innerEligible(kind(),L,m,p,C,S);
+  twoStage=q > 1 && innerEligible(kind(),L,m,p,C,S) &&
+    (m <= 4096 || longStageB(app));
   report(centered ? "fftPadCentered" : "fftPad");
 }
 

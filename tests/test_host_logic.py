@@ -60,8 +60,12 @@ def test_chooser_baseline_configs():
     def params(c, d):
         p = c.params(d)
         return p["m"], p["p"], p["q"]
-    c = fp.HybridConv([1 << 20], [1 << 21])                       # cfg1: two-stage inner
-    assert params(c, 0) == (2048, 512, 1024)
+    c = fp.HybridConv([1 << 20], [1 << 21])       # cfg1: two-stage inner, stage B on long rows
+    assert params(c, 0) == (4096, 256, 512)
+    c = fp.HybridConv([1 << 22], [1 << 23])
+    assert params(c, 0) == (8192, 512, 1024)
+    c = fp.HybridConv([1 << 20], [1 << 21], A=3, B=1, mult=fp.MULT_NONE)   # no long-row stage B
+    assert params(c, 0)[0] <= 4096
     c = fp.HybridConv([4096, 4096], [8192, 8192])                 # cfg2: fused rows at m=4096
     assert params(c, 0) == (4096, 1, 2) and params(c, 1) == (4096, 1, 2)
     c = fp.HybridConv([256] * 3, [384] * 3, family=fp.FAMILY_HERMITIAN)   # cfg3
