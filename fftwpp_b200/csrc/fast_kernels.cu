@@ -1406,7 +1406,7 @@ int manyGeometry(Plan *pl, int lg, uint64_t nrows, ManyGeom& g,
   // threads), a few waves for load balance
   size_t perSM=std::min<size_t>(std::max<size_t>(1,(227*1024)/(g.smem+1024)),
                                 2048/g.nthreads);
-  g.grid=std::min<uint64_t>(g.ntiles,(uint64_t) 148*perSM*4);
+  g.grid=std::min<uint64_t>(g.ntiles,(uint64_t) sm_count()*perSM*4);
   return 1;
 }
 
@@ -1510,7 +1510,7 @@ int launchConvRows(Plan *pl, int lg, void *const *f, int mult, double scale,
   if(smem > SMEM_MAX) return 0;
   uint64_t ngroups=(nrows+ROWS-1)/ROWS;
   if(ngroups == 0) return 1;
-  uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) 148*2*4);
+  uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) sm_count()*2*4);
   int tabid=0;
   int rc=0;
   // p=1, q=2, full rows: the straight-line kernel with register twiddles
@@ -1591,7 +1591,7 @@ int launchConvRowsHerm(Plan *pl, int lg, void *const *f, double scale,
   if(smem > SMEM_MAX) return 0;
   uint64_t ngroups=(nrows+ROWS-1)/ROWS;
   if(ngroups == 0) return 1;
-  uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) 148*2*4);
+  uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) sm_count()*2*4);
   int tabid=0;
   int rc=0;
 #define CALL(LGV)                                                            \

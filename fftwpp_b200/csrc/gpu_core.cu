@@ -878,6 +878,21 @@ void prof_begin(int key, cudaStream_t st)
   g_prof_open=(int) g_prof_recs.size()-1;
 }
 
+// SMs of the current device (grids are sized in multiples of it)
+int sm_count()
+{
+  static int n[16]={0};
+  int dev=0;
+  cudaGetDevice(&dev);
+  int& v=n[dev & 15];
+  if(v == 0) {
+    if(cudaDeviceGetAttribute(&v,cudaDevAttrMultiProcessorCount,dev) !=
+       cudaSuccess || v <= 0)
+      v=148;
+  }
+  return v;
+}
+
 int check_launch(const char *what, cudaStream_t st)
 {
   cudaError_t e=cudaGetLastError();
@@ -1022,7 +1037,7 @@ int launch_scale(double *x, double scale, uint64_t n0, uint64_t n1,
 {
   uint64_t total=n0*n1*n2;
   if(total == 0) return 0;
-  unsigned grid=(unsigned) std::min<uint64_t>((total+255)/256,148*16);
+  unsigned grid=(unsigned) std::min<uint64_t>((total+255)/256,(uint64_t) sm_count()*16);
   prof_begin(3,st);
   scale_kernel<<<grid,256,0,st>>>(x,scale,n0,n1,n2,s0,s1);
   return check_launch("scale_kernel",st);
@@ -1034,7 +1049,7 @@ int launch_copy3(void *dst, const void *src, uint64_t n0, uint64_t n1,
 {
   uint64_t total=n0*n1*n2;
   if(total == 0) return 0;
-  unsigned grid=(unsigned) std::min<uint64_t>((total+255)/256,148*16);
+  unsigned grid=(unsigned) std::min<uint64_t>((total+255)/256,(uint64_t) sm_count()*16);
   prof_begin(3,st);
   copy3_kernel<<<grid,256,0,st>>>((double2 *) dst,(const double2 *) src,
                                    n0,n1,n2,d0,d1,s0,s1);

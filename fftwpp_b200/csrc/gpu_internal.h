@@ -118,6 +118,7 @@ int plan_build(const fftwpp_gpu_pad_desc *d, Plan **out);
 static const int PROF_KEYS=64;
 void prof_begin(int key, cudaStream_t st);
 int check_launch(const char *what, cudaStream_t st);
+int sm_count();
 int prof_enable(int on);
 int prof_read(double *ms, uint64_t *count);
 

@@ -845,15 +845,21 @@ bool tmaRealDisabled()
 #endif
 }
 
-// FFTWPP_TMA_WIDE_REMOTE=0: keep 4-lane tiles for remote destinations (A/B)
+// 8-lane (128-byte row) tiles for remote destinations: measured 2.31 vs 2.51
+// ms per convolution at N=8.  FFTWPP_TMA_WIDE_REMOTE=0 (experiment builds)
+// keeps the 4-lane tiles for A/B timing.
 bool wideRemoteTiles()
 {
+#ifdef FFTWPP_EXPERIMENT_SWITCHES
   static int on=-1;
   if(on < 0) {
     const char *s=getenv("FFTWPP_TMA_WIDE_REMOTE");
     on=(s && *s == '0') ? 0 : 1;
   }
   return on == 1;
+#else
+  return true;
+#endif
 }
 
 bool tmaDisabled()
@@ -886,20 +892,6 @@ int allowSmemTma(K kernel, size_t bytes, int budget=113*1024)
   if(e != cudaSuccess) return cuda_fail(e,"cudaFuncSetAttribute");
   done.push_back(std::make_pair((const void *) kernel,dev));
   return 0;
-}
-
-int smCount()
-{
-  static int n[16]={0};
-  int dev=0;
-  cudaGetDevice(&dev);
-  int& v=n[dev & 15];
-  if(v == 0) {
-    if(cudaDeviceGetAttribute(&v,cudaDevAttrMultiProcessorCount,dev) !=
-       cudaSuccess || v <= 0)
-      v=148;
-  }
-  return v;
 }
 
 // Common eligibility of the direct (uniform complex, one term) passes.
@@ -1067,7 +1059,7 @@ int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
     const int ntc=(d.C+7)/8;
     const long long ntiles=(long long) nrows*ntc;
     const unsigned grid=(unsigned) std::min<long long>(ntiles,
-                                                       (long long) smCount()*2);
+                                                       (long long) sm_count()*2);
     int rc=allowSmemTma(tma_forward_real<9>,smem);
     if(rc) return rc;
     prof_begin(4*pl->tag+0,st);
@@ -1109,7 +1101,7 @@ int tma_try_forward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   const int ntc=(d.C+G::T-1)/G::T;
   const long long ntiles=(long long) nrows*ntc;
   const unsigned grid=(unsigned) std::min<long long>(ntiles,
-                                                     (long long) smCount()*2);
+                                                     (long long) sm_count()*2);
   int rc=allowSmemTma(tma_forward_direct<9>,smem);
   if(rc) return rc;
   prof_begin(4*pl->tag+0,st);
@@ -1154,7 +1146,7 @@ int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
     const int ntc=(d.C+7)/8;
     const long long ntiles=(long long) nrows*ntc;
     const unsigned grid=(unsigned) std::min<long long>(ntiles,
-                                                       (long long) smCount()*2);
+                                                       (long long) sm_count()*2);
     int rc=allowSmemTma(tma_backward_real<9>,smem);
     if(rc) return rc;
     prof_begin(4*pl->tag+1,st);
@@ -1195,7 +1187,7 @@ int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
         const int ntcw=(d.C+W::T-1)/W::T;
         const long long ntilesw=(long long) nrows*ntcw;
         const unsigned gridw=(unsigned) std::min<long long>(ntilesw,
-                                                            (long long) smCount());
+                                                            (long long) sm_count());
         int rcw=allowSmemTma(tma_backward_direct<9,2,512>,smemW,227*1024);
         if(rcw) return rcw;
         prof_begin(4*pl->tag+1,st);
@@ -1234,7 +1226,7 @@ int tma_try_backward(Plan *pl, uint64_t sb0, uint64_t nsb, int layout,
   const int ntc=(d.C+G::T-1)/G::T;
   const long long ntiles=(long long) nrows*ntc;
   const unsigned grid=(unsigned) std::min<long long>(ntiles,
-                                                     (long long) smCount()*2);
+                                                     (long long) sm_count()*2);
   int rc=allowSmemTma(tma_backward_direct<9,2,256>,smem);
   if(rc) return rc;
   prof_begin(4*pl->tag+1,st);

@@ -719,9 +719,7 @@ int launchLongRows(Plan *pl, void *const *f, int mult, double scale,
     if(d.tab[k].n == LR::M && d.tab[k].tw8) tabid=k;
   if(tabid < 0) return 0;
   if(nrows == 0) return 1;
-  int sms=148, dev=0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
+  const int sms=sm_count();
   const uint64_t grid=std::min<uint64_t>(nrows,(uint64_t) sms*(512/LR::NT));
   const size_t smem=((size_t) LR::W1N+LR::BUF)*sizeof(double2);
   int rc=0;
@@ -793,9 +791,7 @@ int tmem_try_convolve(Plan *pl, void *const *f, uint32_t A, uint32_t B,
   if(tabid < 0) return 0;
   const uint64_t ngroups=(nrows+ROWS-1)/ROWS;
   if(ngroups == 0) return 1;
-  int sms=148, dev=0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,dev);
+  const int sms=sm_count();
   const uint64_t grid=std::min<uint64_t>(ngroups,(uint64_t) sms*3);
   const size_t smem=((size_t) RegFFT<9>::twCount()+TPT+(size_t) ROWS*BUF)*
     sizeof(double2);
