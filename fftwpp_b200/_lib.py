@@ -115,6 +115,8 @@ _sig("fftwpp_mpifft_create", c_void_p, c_int, c_int, P(c_size_t), c_int, c_int, 
 _sig("fftwpp_mpifft_destroy", None, c_void_p)
 _sig("fftwpp_mpifft_split", None, c_void_p, P(c_size_t))
 _sig("fftwpp_mpifft_words", c_size_t, c_void_p)
+_sig("fftwpp_mpifft_exchange_table", None, c_void_p, c_int, P(ctypes.c_ulonglong),
+     P(ctypes.c_ulonglong), P(ctypes.c_ulonglong), P(ctypes.c_ulonglong))
 _sig("fftwpp_mpifft_forward", None, c_void_p, c_void_p, c_void_p)
 _sig("fftwpp_mpifft_backward", None, c_void_p, c_void_p, c_void_p)
 _sig("fftwpp_mpifft_normalize", None, c_void_p, c_void_p)

@@ -890,6 +890,18 @@ void fftwpp_mpifft_split(void *fft, size_t *out)
 
 size_t fftwpp_mpifft_words(void *fft) {return ((MpiFft *) fft)->base()->n();}
 
+void fftwpp_mpifft_exchange_table(void *fft, int direction,
+                                  unsigned long long *scount,
+                                  unsigned long long *sdispl,
+                                  unsigned long long *rcount,
+                                  unsigned long long *rdispl)
+{
+  ((MpiFft *) fft)->base()->exchangeTable(direction,(uint64_t *) scount,
+                                          (uint64_t *) sdispl,
+                                          (uint64_t *) rcount,
+                                          (uint64_t *) rdispl);
+}
+
 void fftwpp_mpifft_forward(void *fft, void *in, void *out)
 {
   MpiFft *h=(MpiFft *) fft;

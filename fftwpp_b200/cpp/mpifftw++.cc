@@ -66,6 +66,12 @@ void fftMPIBase::build(size_t X, size_t Y, size_t Z, bool zp)
   // y: contiguous rows (Z == 1) or strided over z inside every x plane
   fy=plainPlan(Y,*app,Z);
   if(zp) fz=plainPlan(Z,*app,1);
+}
+
+// Device scratch is allocated on first use, so that the splits and exchange
+// tables can be queried (and tested) on a host without a CUDA device.
+void fftMPIBase::ready()
+{
   devP.ensure(1,n()*sizeof(Complex));
   work.ensure(1,n()*sizeof(Complex));
 }
@@ -109,6 +115,7 @@ fft2dMPI::fft2dMPI(size_t X, size_t Y, size_t Z, const MPIgroup& group,
 
 void fft2dMPI::iForward(Complex *in, Complex *out)
 {
+  ready();
   if(!out) out=in;
   void *st=gpu::stream();
   if(fz) {
@@ -126,6 +133,7 @@ void fft2dMPI::ForwardWait(Complex *out)
 
 void fft2dMPI::iBackward(Complex *in, Complex *out)
 {
+  ready();
   if(!out) out=in;
   void *st=gpu::stream();
   xpass(-sign,in,work.ptr[0]);
@@ -194,6 +202,7 @@ rcfft2dMPI::~rcfft2dMPI()
 
 void rcfft2dMPI::iForward(double *in, Complex *out)
 {
+  ready();
   void *st=gpu::stream();
   const size_t nr=d.x*rows;
   const size_t lastc=last/2+1;
@@ -212,6 +221,7 @@ void rcfft2dMPI::ForwardWait(Complex *out)
 
 void rcfft2dMPI::iBackward(Complex *in, double *)
 {
+  ready();
   void *st=gpu::stream();
   xpass(1,in,work.ptr[0]);
   transposeForward(work.ptr[0],in,0,1,st);

@@ -46,6 +46,7 @@ protected:
   fftBase *fx,*fy,*fz;
   DeviceArrays work;
   void build(size_t X, size_t Y, size_t Z, bool zpass);
+  void ready(); // allocates the device scratch on first use
   // complex passes of sign sgn; in != out except for xpass
   void zpass(int sgn, const void *in, void *out);
   void ypass(int sgn, const void *in, void *out);

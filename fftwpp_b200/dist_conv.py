@@ -272,6 +272,14 @@ class DistributedFFT:
         self.split = dict(zip("X Y Z x y z x0 y0 z0".split(), [int(v) for v in buf]))
         self.words = int(lib.fftwpp_mpifft_words(self._h))
 
+    def exchange_table(self, direction):
+        """send/receive byte counts and displacements per peer (direction 1:
+        the forward transform's exchange, 0: its inverse)"""
+        n = self.world
+        t = [(ctypes.c_ulonglong * n)() for _ in range(4)]
+        lib.fftwpp_mpifft_exchange_table(self._h, direction, *t)
+        return [[int(v) for v in a] for a in t]
+
     def _shape(self, a, b):
         return (a, b) if len(self.N) == 2 else (a, b, self.split["Z"])
 

@@ -257,6 +257,13 @@ void *fftwpp_mpifft_create(int kind, int dims, const size_t *N, int sign,
 void fftwpp_mpifft_destroy(void *fft);
 void fftwpp_mpifft_split(void *fft, size_t *out);
 size_t fftwpp_mpifft_words(void *fft);
+/* byte counts / displacements of the exchange (direction 1: the forward
+ * transform's x x Y -> X x y, 0: its inverse), for tests; no GPU needed */
+void fftwpp_mpifft_exchange_table(void *fft, int direction,
+                                  unsigned long long *scount,
+                                  unsigned long long *sdispl,
+                                  unsigned long long *rcount,
+                                  unsigned long long *rdispl);
 /* complex: out may be NULL (in place); real: in = double array, out complex */
 void fftwpp_mpifft_forward(void *fft, void *in, void *out);
 /* complex: out may be NULL; real: in complex (overwritten), out doubles */
