@@ -30,6 +30,14 @@
 
 #include <mutex>
 
+// smallest log2(m) served by fast_conv_rows_long.  11 also routes 2048-point
+// rows to it: measured 0.920 vs 0.992 ms for 16384 rows against
+// fast_conv_rows_q2 (profiles/README.md); not the default, because no
+// BASELINE shape uses such rows and only part of the suite ran on that build.
+#ifndef FFTWPP_LONG_MIN_LG
+#define FFTWPP_LONG_MIN_LG 12
+#endif
+
 #ifndef FFTWPP_TMEM_DEFAULT
 #define FFTWPP_TMEM_DEFAULT 0
 #endif
@@ -287,7 +295,7 @@ fast_conv_rows_wtm(PlanDev P, const SubBlockDev *__restrict__ sbs,
 // with multBinary/multcorrelation (convolve.cc:7513-7575,33-110) on
 // fftPad::forward1/backward1 (convolve.cc:849-958,1482-1546), p=1, L <= m.
 
-// m = 16 x SUB (8192 = 16 x 512, 4096 = 16 x 256), SUB threads.  A thread's 16
+// m = 16 x SUB (8192 = 16 x 512, 4096 = 16 x 256, 2048 = 16 x 128), SUB threads.  A thread's 16
 // points are SUB apart, so the first pass is a radix-16 butterfly in
 // registers; ONE CTA-wide exchange then hands every warp whole sub-transforms
 // (8192: one of 512 points, two virtual threads per lane; 4096: two of 256
@@ -313,7 +321,8 @@ struct LongRow16 {
   static const int SUBBUF=SUB+SUB/8;
   static const int BUF=16*SUBBUF;
   static const int NR8=RS::NR8;
-  static_assert(TS == 64 || TS == 32,"one or two sub-transforms per warp");
+  static_assert(TS == 64 || TS == 32 || TS == 16,
+                "a sub-transform must live inside one warp");
 
   // tables: w_M^j, j < SUB | per radix-8 pass i of the sub-transform (legs
   // 2^ls_i apart, ls_i > 0): w_SUB^{j 8^i}, j < 2^ls_i
@@ -326,11 +335,13 @@ struct LongRow16 {
 
   static __device__ __forceinline__ int pad(int p) {return p+(p >> 3);}
   // sub-transform and virtual thread served by array a of this thread
-  static __device__ __forceinline__ int ksub(int warp, int a) {
-    return TS == 64 ? warp : warp+NW*a;
+  // (TS < 32: 32/TS sub-transforms per warp and array, side by side)
+  static __device__ __forceinline__ int ksub(int warp, int lane, int a) {
+    return TS == 64 ? warp : TS == 32 ? warp+NW*a :
+      (2*warp+a)*(32/TS)+lane/TS;
   }
   static __device__ __forceinline__ int tau(int lane, int a) {
-    return TS == 64 ? lane+32*a : lane;
+    return TS == 64 ? lane+32*a : TS == 32 ? lane : lane % TS;
   }
 
   static __device__ __forceinline__ void init(const double2 *tw, double2 *w1s,
@@ -425,13 +436,13 @@ struct LongRow16 {
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        buf[ksub(warp,a)*SUBBUF+pad(RS::pos(tau(lane,a),t,lsFrom))]=x[a][t];
+        buf[ksub(warp,lane,a)*SUBBUF+pad(RS::pos(tau(lane,a),t,lsFrom))]=x[a][t];
     __syncwarp();
 #pragma unroll
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        x[a][t]=buf[ksub(warp,a)*SUBBUF+pad(RS::pos(tau(lane,a),t,lsTo))];
+        x[a][t]=buf[ksub(warp,lane,a)*SUBBUF+pad(RS::pos(tau(lane,a),t,lsTo))];
   }
 
   template<int SIGN>
@@ -476,7 +487,7 @@ struct LongRow16 {
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        x[a][t]=buf[ksub(warp,a)*SUBBUF+pad(tau(lane,a)+TS*t)];
+        x[a][t]=buf[ksub(warp,lane,a)*SUBBUF+pad(tau(lane,a)+TS*t)];
     // the sub-transforms: RegFFT<SUBLG> inside the warp
 #pragma unroll
     for(int i=0; i < NR8; ++i) {
@@ -517,7 +528,7 @@ struct LongRow16 {
     for(int a=0; a < VT; ++a)
 #pragma unroll
       for(int t=0; t < 8; ++t)
-        buf[ksub(warp,a)*SUBBUF+pad(tau(lane,a)+TS*t)]=x[a][t];
+        buf[ksub(warp,lane,a)*SUBBUF+pad(tau(lane,a)+TS*t)]=x[a][t];
     __syncthreads();
 #pragma unroll
     for(int a=0; a < VT; ++a)
@@ -561,7 +572,8 @@ fast_conv_rows_long(PlanDev P, const SubBlockDev *__restrict__ sbs, int nsb,
   const int NT=LR::NT;
   const int VT=LR::VT;
   const int COLS=32*VT;   // TMEM columns of one parked set per warp
-  const int TCOLS=(NT/128)*2*COLS; // of the CTA: NT/128 warps per lane quadrant
+  // of the CTA: NT/128 (at least one) warps per lane quadrant
+  const int TCOLS=(NT >= 128 ? NT/128 : 1)*2*COLS;
   extern __shared__ __align__(16) double2 sm[];
   __shared__ unsigned tmemBase;
   double2 *w1s=sm;
@@ -748,7 +760,8 @@ int tryLongRows(Plan *pl, void *const *f, uint32_t A, uint32_t B, int mult,
 {
   const PlanDev& d=pl->dev;
   const unsigned M=pl->mmax;
-  if((M != 8192 && M != 4096) || d.kind != FFTWPP_KIND_COMPLEX || d.C != 1 ||
+  if((M != 8192 && M != 4096 && M != 2048) || d.kind != FFTWPP_KIND_COMPLEX ||
+     d.C != 1 ||
      d.S != 1 || A != 2 || B != 1)
     return 0;
   if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
@@ -759,7 +772,13 @@ int tryLongRows(Plan *pl, void *const *f, uint32_t A, uint32_t B, int mult,
       return 0;
   if(M == 8192)
     return launchLongRows<LongRow16<13> >(pl,f,mult,scale,nrows,rs,st);
-  return launchLongRows<LongRow16<12> >(pl,f,mult,scale,nrows,rs,st);
+  if(M == 4096)
+    return launchLongRows<LongRow16<12> >(pl,f,mult,scale,nrows,rs,st);
+#if FFTWPP_LONG_MIN_LG <= 11
+  return launchLongRows<LongRow16<11> >(pl,f,mult,scale,nrows,rs,st);
+#else
+  return 0;
+#endif
 }
 
 } // namespace

@@ -28,7 +28,9 @@ def rows_want(f, g, M, corr=False):
                                          (5000, 10000, 8192, True), (4097, 8194, 8192, True),
                                          (8191, 16382, 8192, True), (6144, 16384, 8192, True),
                                          (4096, 8192, 4096, False), (3000, 6000, 4096, True),
-                                         (2049, 4098, 4096, True), (4095, 8190, 4096, True)])
+                                         (2049, 4098, 4096, True), (4095, 8190, 4096, True),
+                                         (2048, 4096, 2048, False), (1500, 3000, 2048, True),
+                                         (1025, 2050, 2048, True)])
 @pytest.mark.parametrize("mult", [fp.MULT_BINARY, fp.MULT_CORRELATION])
 def test_long_rows(L, M, m, force, mult):
     import torch
