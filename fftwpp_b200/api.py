@@ -30,7 +30,21 @@ def _ptr(a):
         if not a.is_contiguous():
             raise ValueError("tensors must be contiguous")
         return a.data_ptr()
-    raise TypeError("expected a numpy array or a torch tensor")
+    # any other device array (cupy, numba, ...): the CUDA array interface
+    cai = getattr(a, "__cuda_array_interface__", None)
+    if cai is not None:
+        if cai.get("strides") is not None:
+            # strides are given only for non-C-contiguous arrays (interface v2+)
+            item = np.dtype(cai["typestr"]).itemsize
+            expect, acc = [], item
+            for n in reversed(cai["shape"]):
+                expect.insert(0, acc)
+                acc *= n
+            if tuple(cai["strides"]) != tuple(expect):
+                raise ValueError("device arrays must be C-contiguous")
+        return int(cai["data"][0])
+    raise TypeError("expected a numpy array, a torch tensor or an object with "
+                    "__cuda_array_interface__")
 
 
 def launch_count():

@@ -144,3 +144,21 @@ def test_no_cpu_fallback():
     assert p.returncode != 0
     assert "SILENT" not in p.stdout
     assert "no CUDA device" in p.stderr or "failed" in p.stderr
+
+
+def test_cuda_array_interface_pointers():
+    """device arrays of other libraries (cupy, numba) reach the C ABI through
+    __cuda_array_interface__; only the pointer extraction is
+    checked here, no device is touched"""
+    from fftwpp_b200.api import _ptr
+
+    class Dev:
+        def __init__(self, shape, strides=None):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<c16", "version": 3,
+                                             "data": (0x7f0000001000, False), "strides": strides}
+    assert _ptr(Dev((4, 8))) == 0x7f0000001000
+    assert _ptr(Dev((4, 8), strides=(128, 16))) == 0x7f0000001000
+    with pytest.raises(ValueError):
+        _ptr(Dev((4, 8), strides=(256, 16)))
+    with pytest.raises(TypeError):
+        _ptr([1, 2, 3])
