@@ -120,6 +120,8 @@ _sig("fftwpp_mpifft_exchange_table", None, c_void_p, c_int, P(ctypes.c_ulonglong
 _sig("fftwpp_mpifft_forward", None, c_void_p, c_void_p, c_void_p)
 _sig("fftwpp_mpifft_backward", None, c_void_p, c_void_p, c_void_p)
 _sig("fftwpp_mpifft_normalize", None, c_void_p, c_void_p)
+_sig("fftwpp_mpifft_shift", None, c_void_p, c_void_p)
+_sig("fftwpp_mpifft_denyquist", None, c_void_p, c_void_p)
 HOST_MULT = ctypes.CFUNCTYPE(None, P(c_void_p), c_size_t, c_void_p, c_size_t)
 DEVICE_MULT = ctypes.CFUNCTYPE(None, P(c_void_p), c_size_t, c_void_p, c_void_p)
 _sig("fftwpp_conv_create_custom", c_void_p, c_int, c_int, P(c_size_t), P(c_size_t),

@@ -916,6 +916,28 @@ void fftwpp_mpifft_backward(void *fft, void *in, void *out)
   else h->r->Backward((Complex *) in,(double *) out);
 }
 
+void fftwpp_mpifft_shift(void *fft, double *f)
+{
+  MpiFft *h=(MpiFft *) fft;
+  if(!h->r) {
+    std::cerr << "fftwpp_mpifft_shift needs a real-to-complex handle"
+              << std::endl;
+    exit(-1);
+  }
+  h->r->Shift(f);
+}
+
+void fftwpp_mpifft_denyquist(void *fft, void *f)
+{
+  MpiFft *h=(MpiFft *) fft;
+  if(!h->r) {
+    std::cerr << "fftwpp_mpifft_denyquist needs a real-to-complex handle"
+              << std::endl;
+    exit(-1);
+  }
+  h->r->deNyquist((Complex *) f);
+}
+
 void fftwpp_mpifft_normalize(void *fft, void *f)
 {
   MpiFft *h=(MpiFft *) fft;

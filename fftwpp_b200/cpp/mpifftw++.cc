@@ -180,6 +180,7 @@ rcfft3dMPI::rcfft3dMPI(const split3& dr, const split3& dc,
 
 void rcfft2dMPI::setup(size_t X, size_t Y, size_t Z)
 {
+  dims3=Z != 0;
   if(Z == 0) { // 2-D: complex x x Yc, Yc split over the ranks
     rows=1;
     last=Y;
@@ -240,6 +241,62 @@ void rcfft2dMPI::BackwardWait(Complex *in, double *out)
   if(nr > 0) // c2r (sign +1)
     gpu::check(fftwpp_gpu_backward(fr->plan(),0,1,1,F,out,0,1.0,nr,lastc,last,
                                    st),"backward (c2r)");
+}
+
+void rcfft2dMPI::Shift(double *f)
+{
+  void *st=gpu::stream();
+  const size_t X=d.X, Y=rows;
+  if(X % 2 || (dims3 && Y % 2)) {
+    std::cerr << (dims3 ? "Shift is not implemented for odd X or odd Y." :
+                  "Shift is not implemented for odd X.") << std::endl;
+    exit(1);
+  }
+  if(d.x == 0) return;
+  if(!dims3) { // 2-D: rows with odd global x
+    const size_t start=(d.x0+1) % 2;
+    if(start < d.x)
+      gpu::check(fftwpp_gpu_scale(f+start*last,-1.0,(d.x-start+1)/2,1,last,
+                                  2*last,0,st),"shift");
+    return;
+  }
+  // 3-D: rows (i,j) with odd x0+i+j
+  for(size_t par=0; par < 2; ++par) { // planes i = par, par+2, ...
+    if(par >= d.x) break;
+    const size_t ystart=(par+d.x0+1) % 2;
+    gpu::check(fftwpp_gpu_scale(f+(par*Y+ystart)*last,-1.0,(d.x-par+1)/2,
+                                (Y-ystart+1)/2,last,2*Y*last,2*last,st),
+               "shift");
+  }
+}
+
+// f[i*pitch+k]=0 for i < rows, k < width (words)
+void rcfft2dMPI::zeroBox(Complex *f, size_t nrows, size_t width, size_t pitch)
+{
+  if(nrows == 0 || width == 0) return;
+  void *st=gpu::stream();
+  ready();
+  gpu::check(fftwpp_gpu_memset(work.ptr[0],0,nrows*width*sizeof(Complex),st),
+             "memset");
+  gpu::check(fftwpp_gpu_memcpy2d(f,pitch*sizeof(Complex),work.ptr[0],
+                                 width*sizeof(Complex),width*sizeof(Complex),
+                                 nrows,2,st),"zero");
+}
+
+void rcfft2dMPI::deNyquist(Complex *f)
+{
+  const size_t X=d.X;
+  if(!dims3) { // 2-D: X x y, y a slice of Y/2+1
+    if(X % 2 == 0) zeroBox(f,1,d.y,d.y);
+    if(last % 2 == 0 && d.y0+d.y == d.Y && d.y > 0)
+      zeroBox(f+d.y-1,X,1,d.y);
+    return;
+  }
+  // 3-D: X x y x Zc
+  const size_t yz=d.y*d.Z;
+  if(X % 2 == 0) zeroBox(f,1,yz,yz);
+  if(rows % 2 == 0 && d.y0 == 0 && d.y > 0) zeroBox(f,X,d.Z,yz);
+  if(last % 2 == 0) zeroBox(f+d.Z-1,X*d.y,1,d.Z);
 }
 
 void rcfft2dMPI::Normalize(double *f)

@@ -20,8 +20,8 @@
  * (out aliased to in with padded rows) are not provided.  The non-blocking
  * pairs exist with the reference's names; the exchange is stream-ordered, so
  * iForward enqueues everything up to and including the exchange and
- * ForwardWait the remaining local pass.  Not provided: Shift/deNyquist and
- * the pencil (split3 xyz) decomposition of fft3dMPI.  Lengths whose largest
+ * ForwardWait the remaining local pass.  Not provided: the pencil (split3
+ * xyz) decomposition of fft3dMPI / rcfft3dMPI.  Lengths whose largest
  * prime factor exceeds 64, or that do not fit one CTA's shared memory
  * (> 8192 points), are refused by the plan builder.
  */
@@ -109,8 +109,26 @@ public:
   }
   void Normalize(double *f);
 
+  // Transforms with the Fourier origin at the centre of x (and y in 3-D):
+  // Shift multiplies the real data by (-1)^x (3-D: (-1)^(x+y)); it needs even
+  // X (and Y), as in the reference (mpifftw++.cc:82-101,165-186).
+  void Shift(double *f);
+  void Forward0(double *in, Complex *out) {
+    Shift(in);
+    Forward(in,out);
+  }
+  void Backward0(Complex *in, double *out) {
+    Backward(in,out);
+    Shift(out);
+  }
+  // Set the Nyquist modes of even shifted transforms to zero, on the
+  // transformed X x y [x Zc] data (mpifftw++.h:345-355,518-538).
+  void deNyquist(Complex *f);
+
 protected:
   rcfft2dMPI(size_t X, size_t Y, size_t Z, const utils::MPIgroup& group);
+  void zeroBox(Complex *f, size_t rows, size_t width, size_t pitch);
+  bool dims3;  // 3-D transform
   size_t rows; // real rows per x plane (2-D: 1, 3-D: Y)
   size_t last; // real row length
   fftBase *fr;

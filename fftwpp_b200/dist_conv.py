@@ -311,6 +311,17 @@ class DistributedFFT:
         lib.fftwpp_mpifft_normalize(self._h, _ptr(f))
         return f
 
+    def shift(self, f):
+        """real=True: f *= (-1)^x (3-D: (-1)^(x+y)) on the real data, which
+        centres the Fourier origin (reference Shift; Forward0 = shift + forward)"""
+        lib.fftwpp_mpifft_shift(self._h, _ptr(f))
+        return f
+
+    def denyquist(self, F):
+        """real=True: zero the Nyquist modes of the transformed data"""
+        lib.fftwpp_mpifft_denyquist(self._h, _ptr(F))
+        return F
+
     def close(self):
         if self._h:
             lib.fftwpp_mpifft_destroy(self._h)

@@ -268,6 +268,11 @@ void fftwpp_mpifft_exchange_table(void *fft, int direction,
 void fftwpp_mpifft_forward(void *fft, void *in, void *out);
 /* complex: out may be NULL; real: in complex (overwritten), out doubles */
 void fftwpp_mpifft_backward(void *fft, void *in, void *out);
+/* kind 1 only: multiply the real x x Y [x Z] data by (-1)^x (3-D: (-1)^(x+y)),
+ * which centres the Fourier origin (reference Shift / Forward0 / Backward0);
+ * zero the Nyquist modes of the transformed data (reference deNyquist) */
+void fftwpp_mpifft_shift(void *fft, double *f);
+void fftwpp_mpifft_denyquist(void *fft, void *f);
 /* divide the x x Y [x Z] data (complex kind 0, real kind 1) by the point count */
 void fftwpp_mpifft_normalize(void *fft, void *f);
 

@@ -94,3 +94,40 @@ def test_real_forward_backward(comm, N):
         assert _err(back.cpu().numpy(), a) < TOL
     finally:
         fft.close()
+
+
+@pytest.mark.parametrize("N", [(8, 8), (16, 12), (6, 9), (4, 6, 10), (16, 16, 16), (8, 4, 7)], ids=str)
+def test_shifted_real_transform_and_denyquist(comm, N):
+    """Forward0 = Shift + Forward (Fourier origin at the centre of x, and y in
+    3-D) and deNyquist (reference mpifftw++.h:345-372,518-560, mpifftw++.cc:82-101,
+    165-186) against the same operations in numpy"""
+    import torch
+    from fftwpp_b200 import dist_conv
+    fft = dist_conv.DistributedFFT(N, 0, 1, real=True, comm=comm)
+    try:
+        a = _rand(N, 11, False)
+        sign = (-1.0) ** np.arange(N[0])
+        sign = sign[:, None] if len(N) == 2 else sign[:, None, None] * ((-1.0) ** np.arange(N[1]))[None, :, None]
+        f = torch.from_numpy(a.copy()).cuda()
+        fft.shift(f)
+        torch.cuda.synchronize()
+        assert np.array_equal(f.cpu().numpy(), a * sign)          # exact sign flips
+        F = fft.buffer()
+        fft.forward(f, F)
+        fft.denyquist(F)
+        torch.cuda.synchronize()
+        want = np.fft.rfftn(a * sign)
+        want[0] = 0                                               # N[0] is even here
+        if len(N) == 2:
+            if N[1] % 2 == 0:
+                want[:, -1] = 0
+        else:
+            if N[1] % 2 == 0:
+                want[:, 0, :] = 0
+            if N[2] % 2 == 0:
+                want[:, :, -1] = 0
+        got = F.cpu().numpy()[:want.size].reshape(want.shape)
+        assert _err(got, want) < TOL
+        assert np.all(got[0] == 0)
+    finally:
+        fft.close()
