@@ -16,7 +16,14 @@ PROGS = ["exampleconv", "exampleconv2", "exampleconv3", "exampleconvh", "example
          "exampleconvh3", "exampleconvr", "exampleconvr2", "exampleconvr3", "cexample",
          "hybridconv", "hybridconv2", "hybridconv3", "hybridconvh", "hybridconvh2",
          "hybridconvh3", "hybridconvr", "hybridconvr2", "hybridconvr3", "hybrid", "hybridh",
-         "hybridr"]
+         "hybridr", "cexample_refwrap"]
+WRAPPER_SYMBOLS = ["create_doubleAlign", "delete_doubleAlign", "create_complexAlign",
+                   "delete_complexAlign", "get_fftwpp_maxthreads", "set_fftwpp_maxthreads",
+                   "fftwpp_HermitianSymmetrize", "fftwpp_HermitianSymmetrizeX",
+                   "fftwpp_HermitianSymmetrizeXY"] + \
+    ["fftwpp_create_%s" % k for k in ("conv1d", "hconv1d", "conv2d", "hconv2d", "conv3d", "hconv3d")] + \
+    ["fftwpp_%s_%s" % (k, op) for k in ("conv1d", "hconv1d", "conv2d", "hconv2d", "conv3d", "hconv3d")
+     for op in ("convolve", "delete")]
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/convolve.h"),
@@ -29,6 +36,26 @@ def test_reference_callers_compile_unmodified():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     for p in PROGS:
         assert os.access(os.path.join(DIR, "_build", p), os.X_OK), p
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/convolve.h"),
+                    reason="reference sources not present on this host")
+def test_reference_wrapper_library_compiles_unmodified():
+    """wrappers/cfftw++.cc itself (the reference's C wrapper LIBRARY, not just its
+    callers) builds against cpp/HybridConvolution.h, convolve.h, Complex.h and
+    cfftw++.h, and exports the 27 symbols of SURVEY 8(b); the C example linked on
+    top of it resolves the wrapper API to that library."""
+    r = subprocess.run(["make", "-C", DIR, "_build/libcfftw_refwrap.so", "_build/cexample_refwrap"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    lib = os.path.join(DIR, "_build", "libcfftw_refwrap.so")
+    nm = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    have = {l.split()[-1] for l in nm.splitlines() if " T " in l}
+    assert set(WRAPPER_SYMBOLS) <= have, sorted(set(WRAPPER_SYMBOLS) - have)
+    ldd = subprocess.run(["ldd", os.path.join(DIR, "_build", "cexample_refwrap")],
+                         capture_output=True, text=True).stdout
+    assert "libcfftw_refwrap.so" in ldd and "lib_fftwpp.so" in ldd
+    assert ldd.index("libcfftw_refwrap.so") < ldd.index("lib_fftwpp.so")
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(DIR, "_build", "hybridconv")),
