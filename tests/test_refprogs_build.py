@@ -7,6 +7,7 @@ CPU-side check: needs the reference sources, so it is skipped where
 tests/test_gpu_refprogs.py)."""
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -70,3 +71,20 @@ def test_reference_caller_fails_loudly_without_gpu():
                        capture_output=True, text=True, timeout=120)
     assert r.returncode != 0
     assert "fftwpp-b200:" in r.stderr  # the library's own error line (cerr + exit)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/wrappers/fftwpp.py"),
+                    reason="reference sources not present on this host")
+def test_reference_python_wrapper_binds_unmodified(tmp_path):
+    """The reference's own wrappers/fftwpp.py loads `lib_fftwpp.so` from the
+    directory it sits in (fftwpp.py:24-26) and sets a prototype on every wrapper
+    symbol at import time.  Placed (here: symlinked, nothing is copied) next to
+    this repository's library, it must import: every symbol it names exists."""
+    (tmp_path / "fftwpp.py").symlink_to("/root/reference/wrappers/fftwpp.py")
+    (tmp_path / "lib_fftwpp.so").symlink_to(os.path.join(ROOT, "fftwpp_b200", "lib_fftwpp.so"))
+    code = ("import sys; sys.path.insert(0, %r); import fftwpp; "
+            "assert fftwpp.base == %r, fftwpp.base; "
+            "print(sorted(fftwpp.__all__), fftwpp.fftwpp_get_maxthreads() >= 1)") % (str(tmp_path), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "['Convolution', 'HConvolution'] True" in r.stdout
