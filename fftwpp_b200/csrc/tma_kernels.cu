@@ -339,8 +339,6 @@ tma_forward_direct(const __grid_constant__ CUtensorMap tmIn,
       fenceAsyncShared();
       __syncthreads();
       if(threadIdx.x == 0) {
-        const long long off=layout ? sb.off_all : sb.off_call;
-        const int r0=(int) (off/P.S);
 #pragma unroll
         for(int b=0; b < G::NBOX; ++b)
           storeSlot(out,isb*G::NBOX+b,buf+b*G::BR*G::T,G::T,2*col0,row);
@@ -505,8 +503,6 @@ tma_forward_real(const __grid_constant__ CUtensorMap tmIn,
       zt[j]=zeta(P,modN(P,k0,j));
   }
   const unsigned tileBytes=M*8*sizeof(double);
-  const int r0a=(int) ((layout ? sbs[0].off_all : sbs[0].off_call)/P.S);
-  const int r0b=(int) ((layout ? sbs[1].off_all : sbs[1].off_call)/P.S);
 
   auto issueLoad=[&](long long tile) {
     const int row=(int) (tile/ntc);
