@@ -765,7 +765,12 @@ int tryLongRows(Plan *pl, void *const *f, uint32_t A, uint32_t B, int mult,
      d.S != 1 || A != 2 || B != 1)
     return 0;
   if(mult != FFTWPP_MULT_BINARY && mult != FFTWPP_MULT_CORRELATION) return 0;
-  if(d.jmin != 0 || d.jmax > (int) M || pl->hsub.empty()) return 0;
+  // one or two sub-blocks (explicit rows, p=1 q=2): the shapes the GPU suite
+  // covers; the kernel's residue loop is general, but longer lists (q > 2)
+  // stay on the kernels of fast_kernels.cu until they are tested here
+  if(d.jmin != 0 || d.jmax > (int) M || pl->hsub.empty() ||
+     pl->hsub.size() > 2)
+    return 0;
   for(size_t i=0; i < pl->hsub.size(); ++i)
     if(pl->hsub[i].mlen != M || pl->hsub[i].nout != M ||
        pl->hsub[i].flags != 0)
